@@ -1,0 +1,214 @@
+/*
+ * ttvdm.h — C ABI of libttvdm_sm100.so: the hand-written sm_100a kernels behind the This&That / SVD
+ * denoising hot path (UNetSpatioTemporalConditionModel + GestureNet ControlNetModel + Euler sampler).
+ *
+ * The reference (Kiteretsu77/This_and_That_VDM) is 100 % Python and has no FFI of its own: every entry
+ * point below replaces a *library-dispatched torch op class* on the hot path. Each declaration cites the
+ * reference call site(s) it stands in for (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer owned by the caller; the library never allocates or frees
+ *     caller memory and never synchronises (all entry points are CUDA-graph capturable);
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - activations are bf16, channels-last: an image batch is [N, H, W, C] == a token matrix [N*H*W, C];
+ *     video rows are ordered (b, f, s) exactly like the reference's `[batch*frames, h*w, C]` tokens;
+ *   - return value: 0 on success, negative ttvdm_status otherwise; ttvdm_last_error() gives the text;
+ *   - no C++ exceptions cross this boundary.
+ */
+#ifndef TTVDM_H_
+#define TTVDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TTVDM_OK = 0,
+  TTVDM_ERR_SHAPE = -1, /* bad shape / alignment / unsupported configuration */
+  TTVDM_ERR_CUDA = -2,  /* CUDA runtime or driver error (see ttvdm_last_error) */
+  TTVDM_ERR_ARCH = -3   /* device is not sm_100 */
+} ttvdm_status;
+
+/* Process-wide immutable state (driver entry points, SM count). Safe to call repeatedly. */
+int ttvdm_init(int device);
+/* Copies the last error message of the calling thread into buf (NUL terminated). */
+int ttvdm_last_error(char* buf, size_t n);
+/* Library / ABI version, bumped when a struct below changes. */
+int ttvdm_abi_version(void);
+/* Number of kernel launches this library has enqueued since load (bench.py's `gpu_launches`). */
+uint64_t ttvdm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1/K2/K3/K4/K15 — one tcgen05 (TMA -> smem -> UMMA -> TMEM) GEMM family with fused epilogue.
+ *
+ *   out = s0 * (A (*) W^T + bias + rowvec[row / rows_per_vec]) + s1 * res1 + s2 * res2
+ *
+ * A-operand addressing modes (the implicit-GEMM part is done by TMA coordinates, never materialised):
+ *   TTVDM_A_LINEAR : A = [M, k1] (optionally concatenated with a2 = [M, k2] along K)
+ *                    replaces nn.Linear q/k/v/o, proj_in/proj_out, FeedForward
+ *                    (svd/diffusion_arch/transformer_temporal.py:235,272,326,373 + diffusers Attention /
+ *                    FeedForward built at :240,:253), 1x1 conv_shortcut of ResnetBlock2D and the 13 zero
+ *                    convs (svd/temporal_controlnet.py:253-297, 616-622)
+ *   TTVDM_A_CONV3X3: A = NHWC [n_img, H, W, k1], 3x3, pad 1, stride 1; W = [N, 9*k1] (tap-major, then
+ *                    channel) replaces nn.Conv2d 3x3: conv_in svd/unet_spatio_temporal_condition.py:133,
+ *                    conv_in_concat svd/temporal_controlnet.py:203, ResnetBlock2D conv1/conv2, Upsample2D
+ *                    conv, conv_out svd/unet_spatio_temporal_condition.py:247
+ *   TTVDM_A_TCONV3 : A = [n_img(=B), H(=F), W(=S), k1], 3 taps over F, zero padded; W = [N, 3*k1]
+ *                    replaces nn.Conv3d (3,1,1) of TemporalResnetBlock (diffusers; built at
+ *                    svd/diffusion_arch/unet_3d_blocks.py:1891,1995,2094,2212,2311)
+ * geglu = 1: weight rows are interleaved (hidden_j, gate_j) and the epilogue writes
+ *            out[:, j] = (acc_2j + b_2j) * gelu_erf(acc_2j+1 + b_2j+1)  (N/2 output columns)
+ *            replaces diffusers GEGLU (Linear(C, 8C) -> chunk -> h * F.gelu(gate)).
+ * ------------------------------------------------------------------------------------------------ */
+enum { TTVDM_A_LINEAR = 0, TTVDM_A_CONV3X3 = 1, TTVDM_A_TCONV3 = 2 };
+
+typedef struct {
+  int mode;          /* TTVDM_A_* */
+  const void* a;     /* bf16 */
+  const void* a2;    /* bf16 or NULL (LINEAR mode only) */
+  int k1, k2;        /* channels of a / a2; multiples of 64 unless a2 == NULL (then k1 % 8 == 0) */
+  int lda, lda2;     /* row (pixel) stride of a / a2 in elements */
+  int n_img, H, W;   /* CONV3X3: images, height, width. TCONV3: B, F, S. LINEAR: ignored */
+  const void* w;     /* bf16 [N, taps*(k1+k2)] */
+  int M, N;          /* rows of the output, output features (before GEGLU halving) */
+  const float* bias;   /* [N] or NULL */
+  const float* rowvec; /* [M / rows_per_vec, N] or NULL */
+  int rows_per_vec;
+  float s0;
+  const void* res1; int ldr1; float s1; /* bf16 [M, *] or NULL */
+  const void* res2; int ldr2; float s2;
+  int geglu;
+  void* out; int ldo; int out_fp32;     /* bf16 (default) or fp32 output, row stride ldo elements */
+} ttvdm_gemm_params;
+
+int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5 — spatial self-attention, flash style on tcgen05 (S and O accumulators in TMEM, online softmax).
+ * q/k/v: bf16 token matrices with row stride ld* (so a fused [M, 3C] qkv buffer works), rows ordered
+ * (image, token); head h uses columns [h*64, h*64+64). softmax(q k^T * scale) v, no mask.
+ * Replaces F.scaled_dot_product_attention in diffusers AttnProcessor2_0 for BasicTransformerBlock.attn1.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  int ldq, ldk, ldv, ldo;
+  int n_img, heads, seq; /* head_dim fixed at 64 */
+  float scale;
+} ttvdm_attn_params;
+int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6/K8 — cross-attention against a short, precomputed context (L <= 128 keys).
+ * q: [rows, heads*64] (row stride ldq). kc/vc: [n_ctx, L, heads*64] bf16 — K/V of the constant context,
+ * projected ONCE per video (reference recomputes them per frame and per pixel,
+ * svd/unet_spatio_temporal_condition.py:452, svd/diffusion_arch/transformer_temporal.py:316-319).
+ * Context of row r:  ctx = (r / ctx_div) % ctx_mod
+ *   spatial  (BasicTransformerBlock.attn2):          ctx_div = F*S, ctx_mod = B         -> ctx = b
+ *   temporal (TemporalBasicTransformerBlock.attn2):  the reference quirk — temporal row (b, s) reads
+ *            context ((b*S + s) mod B) (svd/diffusion_arch/transformer_temporal.py:310-319). The caller
+ *            passes quirk_S = S, quirk_B = B (+ global batch offset) and the kernel derives it per row.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q; const void* kc; const void* vc; void* out;
+  int ldq, ldo;
+  int rows, heads, L;
+  int F, S;          /* rows are ordered (b, f, s); rows = B_local*F*S */
+  int n_ctx;         /* contexts held in kc/vc (global batch B) */
+  int temporal;      /* 0: ctx = b_global ; 1: ctx = (b_global*S + s) mod n_ctx */
+  int batch_offset;  /* global index of the first local batch element (batch sharding) */
+  float scale;
+} ttvdm_xattn_params;
+int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7 — temporal self-attention over the F (<= 32) frames of each (b, s, head); rows ordered (b, f, s),
+ * i.e. the kernel walks frames with stride S*ld instead of materialising the reference's
+ * `(b f) s c -> (b s) f c` permute (diffusers TemporalBasicTransformerBlock.attn1).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  int ldq, ldk, ldv, ldo;
+  int B, F, S, heads;
+  float scale;
+} ttvdm_tattn_params;
+int ttvdm_attn_temporal(const ttvdm_tattn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9/K10 — GroupNorm(32) statistics + apply (+SiLU), channels-last, optional 2-source channel concat
+ * (the up-blocks' torch.cat([hidden, skip], dim=1), svd/diffusion_arch/unet_3d_blocks.py:2242,2352).
+ * A "group instance" spans rows_per_inst consecutive rows: H*W for the per-frame 4-D norm
+ * (ResnetBlock2D.norm1/2, TransformerSpatioTemporalModel.norm, conv_norm_out) and F*H*W for the 5-D
+ * norm of TemporalResnetBlock (stats over all frames of one video).
+ * stats: caller-provided workspace of n_inst*32*2 doubles (sum, sum of squares), zeroed by the call.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x1; int c1; int ld1;
+  const void* x2; int c2; int ld2;  /* NULL / 0 when no concat */
+  int rows; int rows_per_inst;
+  float eps;
+  void* stats;               /* workspace, n_inst*32*2*sizeof(double) bytes */
+  const float* gamma; const float* beta; /* [c1+c2] */
+  int silu;
+  void* out; int ldo;        /* bf16 [rows, c1+c2] */
+} ttvdm_groupnorm_params;
+int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K11 — LayerNorm over C (eps 1e-5) with optional fused "+ frame positional embedding":
+ *   x' = x + addvec[(row / S) % F]      (svd/diffusion_arch/transformer_temporal.py:356 `hidden_states_mix + emb`)
+ *   sum_out = x' (optional), out = LN(x') * gamma + beta
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* x; int ldx; int rows; int C;
+  const float* addvec; int F; int S; /* addvec fp32 [F, C] or NULL */
+  void* sum_out; int ldsum;          /* bf16 or NULL */
+  const float* gamma; const float* beta; float eps;
+  void* out; int ldo;
+} ttvdm_layernorm_params;
+int ttvdm_layernorm(const ttvdm_layernorm_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout helpers around the 3x3 convs.
+ *  im2col_s2 : Downsample2D = Conv2d(C, C, 3, stride 2, pad 1): gathers [n,Ho,Wo,9*C] patches so that
+ *              the conv becomes a LINEAR GEMM (3 calls per network).
+ *  upsample2x: Upsample2D's F.interpolate(scale_factor=2, mode="nearest") in NHWC.
+ * ------------------------------------------------------------------------------------------------ */
+int ttvdm_im2col_s2(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
+int ttvdm_upsample2x(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
+/* out[r, :] = a[r, :] + scale * b[r, :]  (U4: ControlNet residual merge, svd/unet_spatio_temporal_condition.py:485-502) */
+int ttvdm_axpy(const void* a, const void* b, void* out, float scale, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K14 — sampler glue (svd/pipeline_stable_video_diffusion_controlnet.py:626-635, 697-709 and diffusers
+ * EulerDiscreteScheduler.scale_model_input / step, v-prediction).
+ *  prepare: model_in[b, f, h, w, 0:64] (bf16, channel-padded NHWC) =
+ *           [ latents[f, 0:4] / sqrt(sigma^2+1) | image_latents[b, 0:4] | cond[f, 0:4] (or 0) | 0... ]
+ *           latents fp32 [F,4,h,w] (reference NCHW state), image_latents fp32 [B,4,h,w], cond fp32 [F,4,h,w].
+ *  step   : eps = uncond + g[f] * (cond - uncond); x0 = eps * (-sigma/sqrt(sigma^2+1)) + x/(sigma^2+1);
+ *           x += (x - x0)/sigma * (sigma_next - sigma)           (all fp32, in place on latents)
+ *           eps_u / eps_c: fp32 [F*h*w, 4] channels-last network outputs of the two CFG halves.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* latents; const float* image_latents; const float* cond; /* cond may be NULL */
+  void* model_in; int c_pad; /* bf16 [B_local, F, h, w, c_pad] */
+  int B_local; int batch_offset; int F; int h; int w;
+  float sigma;
+} ttvdm_prepare_params;
+int ttvdm_sampler_prepare(const ttvdm_prepare_params* p, void* stream);
+
+typedef struct {
+  float* latents;                       /* fp32 [F,4,h,w], updated in place */
+  const float* eps_u; const float* eps_c; int ld_eps; /* fp32 channels-last [F*h*w, ld_eps] */
+  const float* guidance;                /* fp32 [F] */
+  int F; int h; int w;
+  float sigma; float sigma_next;
+} ttvdm_euler_params;
+int ttvdm_sampler_euler_step(const ttvdm_euler_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTVDM_H_ */

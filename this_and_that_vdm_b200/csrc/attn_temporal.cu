@@ -1,0 +1,124 @@
+// K7 — temporal self-attention: F (<= 16) frames x F frames per (b, s, head), head_dim 64. ~0.05 % of the FLOPs
+// and HBM-bound, so: shared-memory K/V staging, one query frame per thread, no tensor cores. Rows stay in the
+// (b, f, s) token order — frames are walked with stride S*ld instead of permuting the activation.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ttvdm {
+
+constexpr int kTaItemsPerCta = 8;  // 4 warps x 2 items
+constexpr int kTaMaxF = 16;
+
+__global__ void __launch_bounds__(128)
+attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                     const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int ldq, int ldk, int ldv,
+                     int ldo, int B, int F, int S, int heads, float scale) {
+  __shared__ __align__(16) uint32_t sk[kTaItemsPerCta][kTaMaxF][32];
+  __shared__ __align__(16) uint32_t sv[kTaItemsPerCta][kTaMaxF][32];
+  const int slot = threadIdx.x >> 4;  // item slot within the CTA
+  const int l16 = threadIdx.x & 15;
+  const long long items = (long long)B * S * heads;
+  const long long item = (long long)blockIdx.x * kTaItemsPerCta + slot;
+  const bool item_ok = item < items;
+  int head = 0, s = 0, b = 0;
+  if (item_ok) {
+    head = (int)(item % heads);
+    const long long bs = item / heads;
+    s = (int)(bs % S);
+    b = (int)(bs / S);
+  }
+  const long long row0 = ((long long)b * F) * S + s;  // frame 0 row; frame f is row0 + f*S
+  if (item_ok) {
+    for (int f = 0; f < F; ++f) {
+      const long long row = row0 + (long long)f * S;
+      const uint2 kk = __ldg(reinterpret_cast<const uint2*>(k + row * ldk + head * 64) + l16);
+      const uint2 vv = __ldg(reinterpret_cast<const uint2*>(v + row * ldv + head * 64) + l16);
+      sk[slot][f][l16 * 2] = kk.x;
+      sk[slot][f][l16 * 2 + 1] = kk.y;
+      sv[slot][f][l16 * 2] = vv.x;
+      sv[slot][f][l16 * 2 + 1] = vv.y;
+    }
+  }
+  __syncthreads();
+  if (!item_ok || l16 >= F) return;
+  const long long qrow = row0 + (long long)l16 * S;
+  float qf[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + qrow * ldq + head * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = __ldg(qp + i);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f2 = unpack_bf16(w4[j]);
+        qf[i * 8 + j * 2] = f2.x * scale;
+        qf[i * 8 + j * 2 + 1] = f2.y * scale;
+      }
+    }
+  }
+  float sc[kTaMaxF];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kTaMaxF; ++j) {
+    if (j < F) {
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        const float2 kk = unpack_bf16(sk[slot][j][d]);
+        acc += qf[2 * d] * kk.x + qf[2 * d + 1] * kk.y;
+      }
+      sc[j] = acc;
+      mx = fmaxf(mx, acc);
+    } else {
+      sc[j] = -INFINITY;
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTaMaxF; ++j) {
+    sc[j] = (j < F) ? __expf(sc[j] - mx) : 0.f;
+    sum += sc[j];
+  }
+  const float inv = 1.f / sum;
+  float o[64];
+#pragma unroll
+  for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTaMaxF; ++j) {
+    if (j < F) {
+      const float pj = sc[j] * inv;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        const float2 vv = unpack_bf16(sv[slot][j][d]);
+        o[2 * d] += pj * vv.x;
+        o[2 * d + 1] += pj * vv.y;
+      }
+    }
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + qrow * ldo + head * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    op[i] = make_uint4(pack_bf16(o[i * 8], o[i * 8 + 1]), pack_bf16(o[i * 8 + 2], o[i * 8 + 3]),
+                       pack_bf16(o[i * 8 + 4], o[i * 8 + 5]), pack_bf16(o[i * 8 + 6], o[i * 8 + 7]));
+}
+
+}  // namespace ttvdm
+
+using namespace ttvdm;
+
+extern "C" int ttvdm_attn_temporal(const ttvdm_tattn_params* p, void* stream_) {
+  if (int rc = ensure_init()) return rc;
+  if (!p || !p->q || !p->k || !p->v || !p->out) return fail(TTVDM_ERR_SHAPE, "attn_temporal: null");
+  if (p->F < 1 || p->F > kTaMaxF) return fail(TTVDM_ERR_SHAPE, "attn_temporal: F=%d (max %d)", p->F, kTaMaxF);
+  if ((p->ldq | p->ldk | p->ldv | p->ldo) % 8 != 0) return fail(TTVDM_ERR_SHAPE, "attn_temporal: ld %% 8 != 0");
+  const long long items = (long long)p->B * p->S * p->heads;
+  if (items <= 0) return fail(TTVDM_ERR_SHAPE, "attn_temporal: empty");
+  const int grid = (int)((items + kTaItemsPerCta - 1) / kTaItemsPerCta);
+  attn_temporal_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(p->q), static_cast<const __nv_bfloat16*>(p->k),
+      static_cast<const __nv_bfloat16*>(p->v), static_cast<__nv_bfloat16*>(p->out), p->ldq, p->ldk, p->ldv, p->ldo,
+      p->B, p->F, p->S, p->heads, p->scale);
+  TTVDM_CHECK_LAUNCH("attn_temporal_kernel");
+  return 0;
+}

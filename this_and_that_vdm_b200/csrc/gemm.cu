@@ -1,0 +1,498 @@
+// ttvdm_gemm — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   warp 0      : TMA producer (A tile 128 x 64 bf16 + B tile BN x 64 bf16 per stage, 128B swizzle)
+//   warp 1      : MMA issuer (one lane issues tcgen05.mma, M=128, N=BN, K=16; accumulators in TMEM)
+//   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x up to 256 columns)
+//   warp 3      : idle
+//   warps 4..11 : epilogue (TMEM -> registers -> fused bias / timestep shift / residuals / GEGLU -> global)
+//
+// The 3x3 and temporal convolutions never materialise im2col: the producer shifts the TMA box coordinates per
+// filter tap and lets TMA zero-fill the halo (out-of-bounds) elements.
+#include <cstring>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ttvdm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kNumThreads = 384;
+constexpr int kAccCols = 256;  // TMEM columns per accumulator stage
+constexpr int kSmemBudget = 232448;
+
+struct GemmArgs {
+  int mode;
+  int M, N;
+  int kc_a1;       // 64-wide K chunks served by tensor map A (rest of a tap: map A2)
+  int kc_per_tap;  // K chunks per filter tap
+  int taps;        // 1, 9 or 3
+  int block_n, stages;
+  int m_tiles, n_tiles;
+  // conv / tconv geometry
+  int H, W, TW, TH, tiles_w, tiles_h;
+  // epilogue
+  const float* bias;
+  const float* rowvec;
+  int rows_per_vec;
+  float s0, s1, s2;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  int ldr1, ldr2;
+  int geglu;
+  void* out;
+  int ldo, out_fp32;
+};
+
+struct TileCoord {
+  int n0;          // first output column
+  int m0;          // LINEAR: first row
+  int img, h0, w0; // CONV: image, first row/col of the TH x TW pixel box; TCONV: img=b, h0=f, w0=s0
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
+  TileCoord t;
+  const int mt = tile / g.n_tiles;
+  t.n0 = (tile - mt * g.n_tiles) * g.block_n;
+  t.m0 = mt * kBlockM;
+  t.img = 0;
+  t.h0 = 0;
+  t.w0 = 0;
+  if (g.mode == TTVDM_A_CONV3X3) {
+    const int per_img = g.tiles_w * g.tiles_h;
+    t.img = mt / per_img;
+    const int r = mt - t.img * per_img;
+    const int th = r / g.tiles_w;
+    t.h0 = th * g.TH;
+    t.w0 = (r - th * g.tiles_w) * g.TW;
+  } else if (g.mode == TTVDM_A_TCONV3) {
+    // tiles_w = tiles per frame along S; H = F; W = S
+    const int per_img = g.tiles_w * g.H;
+    t.img = mt / per_img;
+    const int r = mt - t.img * per_img;
+    t.h0 = r / g.tiles_w;
+    t.w0 = (r - t.h0 * g.tiles_w) * kBlockM;
+  }
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], long long out_row, int col0,
+                                               const float* rv) {
+    float a[32];
+    const bool full = (col0 + 32 <= g.N) && ((g.N & 7) == 0);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+    if (g.bias != nullptr) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0 + i));
+          a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) a[i] += g.bias[col0 + i];
+      }
+    }
+    if (rv != nullptr) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + i));
+          a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) a[i] += rv[col0 + i];
+      }
+    }
+    if (g.geglu) {
+      // interleaved (hidden, gate) columns -> 16 outputs
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + (col0 >> 1);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o0 = a[4 * j] * gelu_erf(a[4 * j + 1]);
+        const float o1 = a[4 * j + 2] * gelu_erf(a[4 * j + 3]);
+        pk[j] = pack_bf16(g.s0 * o0, g.s0 * o1);
+      }
+      if (full) {
+        uint4* o4 = reinterpret_cast<uint4*>(o);
+        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+        for (int j = 0; j < 16; ++j)
+          if (col0 + 2 * j + 1 < g.N) {
+            const float2 f = unpack_bf16(pk[j >> 1]);
+            o[j] = __float2bfloat16((j & 1) ? f.y : f.x);
+          }
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] *= g.s0;
+    if (g.res1 != nullptr) {
+      const __nv_bfloat16* rp = g.res1 + out_row * g.ldr1 + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16(w4[j]);
+            a[i * 8 + j * 2] += g.s1 * f.x;
+            a[i * 8 + j * 2 + 1] += g.s1 * f.y;
+          }
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) a[i] += g.s1 * __bfloat162float(rp[i]);
+      }
+    }
+    if (g.res2 != nullptr) {
+      const __nv_bfloat16* rp = g.res2 + out_row * g.ldr2 + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16(w4[j]);
+            a[i * 8 + j * 2] += g.s2 * f.x;
+            a[i * 8 + j * 2 + 1] += g.s2 * f.y;
+          }
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) a[i] += g.s2 * __bfloat162float(rp[i]);
+      }
+    }
+    if (g.out_fp32) {
+      float* o = reinterpret_cast<float*>(g.out) + out_row * g.ldo + col0;
+      if (full && (g.ldo & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) o[i] = a[i];
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col0;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *(reinterpret_cast<uint4*>(o) + i) =
+              make_uint4(pack_bf16(a[i * 8], a[i * 8 + 1]), pack_bf16(a[i * 8 + 2], a[i * 8 + 3]),
+                         pack_bf16(a[i * 8 + 4], a[i * 8 + 5]), pack_bf16(a[i * 8 + 6], a[i * 8 + 7]));
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < g.N) o[i] = __float2bfloat16(a[i]);
+      }
+    }
+  }
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* tiles = smem + 1024;
+  const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.m_tiles * g.n_tiles;
+  const int num_kc = g.taps * g.kc_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const TileCoord t = tile_coord(g, tile);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = tiles + stage * stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          const int tap = kc / g.kc_per_tap;
+          const int cc = kc - tap * g.kc_per_tap;
+          if (g.mode == TTVDM_A_LINEAR) {
+            if (cc < g.kc_a1)
+              tma_load_2d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.m0);
+            else
+              tma_load_2d(sa, &tmA2, &full_bar[stage], (cc - g.kc_a1) * kBlockK, t.m0);
+          } else if (g.mode == TTVDM_A_CONV3X3) {
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
+          } else {
+            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
+        }
+        __syncwarp();
+        if (++stage == g.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(kBlockM, g.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      for (int kc = 0; kc < num_kc; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (kc == num_kc - 1) tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == g.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2; // which 32-column chunks (even / odd)
+    const int chunks = g.block_n / 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const TileCoord t = tile_coord(g, tile);
+      const int r = q * 32 + lane;
+      long long out_row;
+      bool valid;
+      if (g.mode == TTVDM_A_LINEAR) {
+        out_row = t.m0 + r;
+        valid = out_row < g.M;
+      } else if (g.mode == TTVDM_A_CONV3X3) {
+        const int th = r / g.TW, tw = r - th * g.TW;
+        const int h = t.h0 + th, w = t.w0 + tw;
+        valid = (h < g.H) && (w < g.W);
+        out_row = ((long long)t.img * g.H + h) * g.W + w;
+      } else {
+        const int s = t.w0 + r;
+        valid = s < g.W;
+        out_row = ((long long)t.img * g.H + t.h0) * g.W + s;
+      }
+      const float* rv = nullptr;
+      if (g.rowvec != nullptr && valid) rv = g.rowvec + (out_row / g.rows_per_vec) * g.N;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int ch = half; ch < chunks; ch += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kAccCols + ch * 32, v);
+        tmem_ld_wait();
+        const int col0 = t.n0 + ch * 32;
+        if (valid && col0 < g.N) epilogue_chunk(g, v, out_row, col0, rv);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+static int pick_block_n(int N) {
+  // largest UMMA-legal tile (multiple of 32 for the epilogue chunks, <= 256) that divides N; else 128/64/32
+  const int cands[] = {256, 192, 160, 128, 96, 64, 32};
+  for (int c : cands)
+    if (N % c == 0) return c;
+  if (N >= 128) return 128;
+  if (N >= 64) return 64;
+  return 32;
+}
+
+}  // namespace ttvdm
+
+using namespace ttvdm;
+
+extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!p || !p->a || !p->w || !p->out) return fail(TTVDM_ERR_SHAPE, "gemm: null pointer");
+  if (p->M <= 0 || p->N <= 0) return fail(TTVDM_ERR_SHAPE, "gemm: empty problem M=%d N=%d", p->M, p->N);
+  const int k2 = p->a2 ? p->k2 : 0;
+  if (p->k1 % kBlockK != 0 || k2 % kBlockK != 0)
+    return fail(TTVDM_ERR_SHAPE, "gemm: k1=%d / k2=%d must be multiples of 64", p->k1, k2);
+  if (p->a2 && p->mode != TTVDM_A_LINEAR) return fail(TTVDM_ERR_SHAPE, "gemm: a2 only in LINEAR mode");
+  if (p->geglu && (p->N % 2 != 0 || p->res1 || p->res2 || p->out_fp32))
+    return fail(TTVDM_ERR_SHAPE, "gemm: geglu epilogue excludes residuals / fp32 out");
+  if (p->rowvec && p->rows_per_vec <= 0) return fail(TTVDM_ERR_SHAPE, "gemm: rows_per_vec must be > 0");
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.mode = p->mode;
+  g.M = p->M;
+  g.N = p->N;
+  g.kc_a1 = p->k1 / kBlockK;
+  g.kc_per_tap = (p->k1 + k2) / kBlockK;
+  g.taps = p->mode == TTVDM_A_CONV3X3 ? 9 : (p->mode == TTVDM_A_TCONV3 ? 3 : 1);
+  g.block_n = pick_block_n(p->N);
+  g.n_tiles = (p->N + g.block_n - 1) / g.block_n;
+  const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
+  g.stages = (kSmemBudget - 2048) / stage_bytes;
+  if (g.stages > kMaxStages) g.stages = kMaxStages;
+  const int ktot = g.taps * (p->k1 + k2);
+
+  CUtensorMap tmA, tmA2, tmB;
+  int rc;
+  if (p->mode == TTVDM_A_LINEAR) {
+    g.m_tiles = (p->M + kBlockM - 1) / kBlockM;
+    uint64_t dims[2] = {(uint64_t)p->k1, (uint64_t)p->M};
+    uint64_t str[1] = {(uint64_t)p->lda * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if ((rc = make_tmap_bf16(&tmA, p->a, 2, dims, str, box))) return rc;
+    if (p->a2) {
+      uint64_t dims2[2] = {(uint64_t)k2, (uint64_t)p->M};
+      uint64_t str2[1] = {(uint64_t)p->lda2 * 2};
+      if ((rc = make_tmap_bf16(&tmA2, p->a2, 2, dims2, str2, box))) return rc;
+    } else {
+      tmA2 = tmA;
+    }
+  } else if (p->mode == TTVDM_A_CONV3X3) {
+    if ((long long)p->n_img * p->H * p->W != p->M) return fail(TTVDM_ERR_SHAPE, "conv3x3: M != n_img*H*W");
+    // pick the TW x TH (=128) pixel box wasting the fewest MMA rows
+    int best_tw = 128;
+    double best_eff = -1.0;
+    for (int tw = 128; tw >= 1; tw >>= 1) {
+      const int th = 128 / tw;
+      const double cover = (double)((p->W + tw - 1) / tw * tw) * ((p->H + th - 1) / th * th);
+      const double eff = (double)p->W * p->H / cover;
+      if (eff > best_eff + 1e-9) {
+        best_eff = eff;
+        best_tw = tw;
+      }
+    }
+    g.TW = best_tw;
+    g.TH = 128 / best_tw;
+    g.H = p->H;
+    g.W = p->W;
+    g.tiles_w = (p->W + g.TW - 1) / g.TW;
+    g.tiles_h = (p->H + g.TH - 1) / g.TH;
+    g.m_tiles = p->n_img * g.tiles_w * g.tiles_h;
+    uint64_t dims[4] = {(uint64_t)p->k1, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->n_img};
+    uint64_t str[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * p->W, (uint64_t)p->lda * 2 * p->W * p->H};
+    uint32_t box[4] = {kBlockK, (uint32_t)g.TW, (uint32_t)g.TH, 1};
+    if ((rc = make_tmap_bf16(&tmA, p->a, 4, dims, str, box))) return rc;
+    tmA2 = tmA;
+  } else if (p->mode == TTVDM_A_TCONV3) {
+    if ((long long)p->n_img * p->H * p->W != p->M) return fail(TTVDM_ERR_SHAPE, "tconv3: M != B*F*S");
+    g.H = p->H;  // F
+    g.W = p->W;  // S
+    g.tiles_w = (p->W + kBlockM - 1) / kBlockM;
+    g.m_tiles = p->n_img * p->H * g.tiles_w;
+    uint64_t dims[4] = {(uint64_t)p->k1, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->n_img};
+    uint64_t str[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * p->W, (uint64_t)p->lda * 2 * p->W * p->H};
+    uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
+    if ((rc = make_tmap_bf16(&tmA, p->a, 4, dims, str, box))) return rc;
+    tmA2 = tmA;
+  } else {
+    return fail(TTVDM_ERR_SHAPE, "gemm: unknown mode %d", p->mode);
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)p->N};
+    uint64_t str[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {kBlockK, (uint32_t)g.block_n};
+    if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box))) return rc;
+  }
+  g.bias = p->bias;
+  g.rowvec = p->rowvec;
+  g.rows_per_vec = p->rows_per_vec > 0 ? p->rows_per_vec : 1;
+  g.s0 = p->s0;
+  g.s1 = p->s1;
+  g.s2 = p->s2;
+  g.res1 = static_cast<const __nv_bfloat16*>(p->res1);
+  g.res2 = static_cast<const __nv_bfloat16*>(p->res2);
+  g.ldr1 = p->ldr1;
+  g.ldr2 = p->ldr2;
+  g.geglu = p->geglu;
+  g.out = p->out;
+  g.ldo = p->ldo;
+  g.out_fp32 = p->out_fp32;
+  // vector epilogue needs 16 B aligned rows; otherwise the scalar path is taken only for ragged columns
+  if (!p->out_fp32 && ((p->ldo % 8) != 0 && p->N >= 32)) return fail(TTVDM_ERR_SHAPE, "gemm: ldo %% 8 != 0");
+  if ((p->res1 && p->ldr1 % 8) || (p->res2 && p->ldr2 % 8)) return fail(TTVDM_ERR_SHAPE, "gemm: ldr %% 8 != 0");
+
+  const size_t smem = 2048 + (size_t)g.stages * stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_tiles = g.m_tiles * g.n_tiles;
+  const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, g);
+  TTVDM_CHECK_LAUNCH("gemm_kernel");
+  return 0;
+}

@@ -1,0 +1,257 @@
+"""ctypes binding of libttvdm_sm100.so (C ABI in include/ttvdm.h).
+
+Only raw device pointers, sizes and the CUDA stream cross this boundary; torch is used purely as the owner of
+device memory. There is no CPU fallback: if the shared library is missing or the device is not sm_100 every
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "libttvdm_sm100.so"
+
+A_LINEAR, A_CONV3X3, A_TCONV3 = 0, 1, 2
+
+c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("mode", c_int), ("a", c_void_p), ("a2", c_void_p), ("k1", c_int), ("k2", c_int),
+        ("lda", c_int), ("lda2", c_int), ("n_img", c_int), ("H", c_int), ("W", c_int),
+        ("w", c_void_p), ("M", c_int), ("N", c_int),
+        ("bias", c_void_p), ("rowvec", c_void_p), ("rows_per_vec", c_int), ("s0", c_float),
+        ("res1", c_void_p), ("ldr1", c_int), ("s1", c_float),
+        ("res2", c_void_p), ("ldr2", c_int), ("s2", c_float),
+        ("geglu", c_int), ("out", c_void_p), ("ldo", c_int), ("out_fp32", c_int),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
+        ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldo", c_int),
+        ("n_img", c_int), ("heads", c_int), ("seq", c_int), ("scale", c_float),
+    ]
+
+
+class XAttnParams(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("kc", c_void_p), ("vc", c_void_p), ("out", c_void_p),
+        ("ldq", c_int), ("ldo", c_int), ("rows", c_int), ("heads", c_int), ("L", c_int),
+        ("F", c_int), ("S", c_int), ("n_ctx", c_int), ("temporal", c_int), ("batch_offset", c_int),
+        ("scale", c_float),
+    ]
+
+
+class TAttnParams(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
+        ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldo", c_int),
+        ("B", c_int), ("F", c_int), ("S", c_int), ("heads", c_int), ("scale", c_float),
+    ]
+
+
+class GroupNormParams(C.Structure):
+    _fields_ = [
+        ("x1", c_void_p), ("c1", c_int), ("ld1", c_int),
+        ("x2", c_void_p), ("c2", c_int), ("ld2", c_int),
+        ("rows", c_int), ("rows_per_inst", c_int), ("eps", c_float),
+        ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("silu", c_int),
+        ("out", c_void_p), ("ldo", c_int),
+    ]
+
+
+class LayerNormParams(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("ldx", c_int), ("rows", c_int), ("C", c_int),
+        ("addvec", c_void_p), ("F", c_int), ("S", c_int),
+        ("sum_out", c_void_p), ("ldsum", c_int),
+        ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
+        ("out", c_void_p), ("ldo", c_int),
+    ]
+
+
+class PrepareParams(C.Structure):
+    _fields_ = [
+        ("latents", c_void_p), ("image_latents", c_void_p), ("cond", c_void_p),
+        ("model_in", c_void_p), ("c_pad", c_int),
+        ("B_local", c_int), ("batch_offset", c_int), ("F", c_int), ("h", c_int), ("w", c_int),
+        ("sigma", c_float),
+    ]
+
+
+class EulerParams(C.Structure):
+    _fields_ = [
+        ("latents", c_void_p), ("eps_u", c_void_p), ("eps_c", c_void_p), ("ld_eps", c_int),
+        ("guidance", c_void_p), ("F", c_int), ("h", c_int), ("w", c_int),
+        ("sigma", c_float), ("sigma_next", c_float),
+    ]
+
+
+EXPORTS = [
+    "ttvdm_init", "ttvdm_last_error", "ttvdm_abi_version", "ttvdm_launch_count",
+    "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
+    "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy",
+    "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step",
+]
+
+_lib: Optional[C.CDLL] = None
+_inited_devices: set[int] = set()
+
+
+class TtvdmError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (no compute). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise TtvdmError(
+                f"{LIB_PATH} is missing: run `python -m this_and_that_vdm_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        lib.ttvdm_launch_count.restype = C.c_uint64
+        for name in EXPORTS:
+            getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        buf = C.create_string_buffer(512)
+        load().ttvdm_last_error(buf, 512)
+        raise TtvdmError(f"{what} failed (status {rc}): {buf.value.decode(errors='replace')}")
+
+
+def init(device: Optional[int] = None) -> None:
+    if not torch.cuda.is_available():
+        raise TtvdmError("ttvdm needs a CUDA device (sm_100); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else device
+    if dev not in _inited_devices:
+        _check(load().ttvdm_init(dev), "ttvdm_init")
+        _inited_devices.add(dev)
+
+
+def launch_count() -> int:
+    return int(load().ttvdm_launch_count())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def call(name: str, params: C.Structure) -> None:
+    _check(getattr(load(), name)(C.byref(params), _stream()), name)
+
+
+def call_raw(name: str, *args) -> None:
+    _check(getattr(load(), name)(*args, _stream()), name)
+
+
+# ------------------------------------------------------------------------------------------------ wrappers
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, k1: int,
+         mode: int = A_LINEAR, lda: Optional[int] = None, a2: Optional[torch.Tensor] = None, k2: int = 0,
+         lda2: int = 0, n_img: int = 0, H: int = 0, W: int = 0, bias: Optional[torch.Tensor] = None,
+         rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0, s0: float = 1.0,
+         res1: Optional[torch.Tensor] = None, ldr1: int = 0, s1: float = 1.0,
+         res2: Optional[torch.Tensor] = None, ldr2: int = 0, s2: float = 1.0,
+         geglu: bool = False, ldo: Optional[int] = None, out_fp32: bool = False) -> None:
+    p = GemmParams()
+    p.mode = mode
+    p.a, p.a2, p.k1, p.k2 = _ptr(a), _ptr(a2), k1, k2
+    p.lda = k1 if lda is None else lda
+    p.lda2 = lda2 if lda2 else k2
+    p.n_img, p.H, p.W = n_img, H, W
+    p.w, p.M, p.N = _ptr(w), M, N
+    p.bias, p.rowvec, p.rows_per_vec, p.s0 = _ptr(bias), _ptr(rowvec), rows_per_vec, s0
+    p.res1, p.ldr1, p.s1 = _ptr(res1), ldr1 if ldr1 else N, s1
+    p.res2, p.ldr2, p.s2 = _ptr(res2), ldr2 if ldr2 else N, s2
+    p.geglu = int(geglu)
+    p.out = _ptr(out)
+    p.ldo = ldo if ldo is not None else (N // 2 if geglu else N)
+    p.out_fp32 = int(out_fp32)
+    call("ttvdm_gemm", p)
+
+
+def attn_spatial(q, k, v, out, *, ldq, ldk, ldv, ldo, n_img, heads, seq, scale) -> None:
+    p = AttnParams()
+    p.q, p.k, p.v, p.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
+    p.ldq, p.ldk, p.ldv, p.ldo = ldq, ldk, ldv, ldo
+    p.n_img, p.heads, p.seq, p.scale = n_img, heads, seq, scale
+    call("ttvdm_attn_spatial", p)
+
+
+def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale) -> None:
+    p = XAttnParams()
+    p.q, p.kc, p.vc, p.out = _ptr(q), _ptr(kc), _ptr(vc), _ptr(out)
+    p.ldq, p.ldo, p.rows, p.heads, p.L = ldq, ldo, rows, heads, L
+    p.F, p.S, p.n_ctx, p.temporal, p.batch_offset, p.scale = F, S, n_ctx, int(temporal), batch_offset, scale
+    call("ttvdm_attn_cross", p)
+
+
+def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) -> None:
+    p = TAttnParams()
+    p.q, p.k, p.v, p.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
+    p.ldq, p.ldk, p.ldv, p.ldo = ldq, ldk, ldv, ldo
+    p.B, p.F, p.S, p.heads, p.scale = B, F, S, heads, scale
+    call("ttvdm_attn_temporal", p)
+
+
+def groupnorm(x1, out, stats, gamma, beta, *, c1, rows, rows_per_inst, eps, silu, x2=None, c2=0,
+              ld1=None, ld2=None, ldo=None) -> None:
+    p = GroupNormParams()
+    p.x1, p.c1, p.ld1 = _ptr(x1), c1, c1 if ld1 is None else ld1
+    p.x2, p.c2, p.ld2 = _ptr(x2), c2, c2 if ld2 is None else ld2
+    p.rows, p.rows_per_inst, p.eps = rows, rows_per_inst, eps
+    p.stats, p.gamma, p.beta, p.silu = _ptr(stats), _ptr(gamma), _ptr(beta), int(silu)
+    p.out, p.ldo = _ptr(out), (c1 + c2) if ldo is None else ldo
+    call("ttvdm_groupnorm", p)
+
+
+def layernorm(x, out, gamma, beta, *, rows, C, eps=1e-5, addvec=None, F=0, S=0, sum_out=None,
+              ldx=None, ldo=None, ldsum=None) -> None:
+    p = LayerNormParams()
+    p.x, p.ldx, p.rows, p.C = _ptr(x), C if ldx is None else ldx, rows, C
+    p.addvec, p.F, p.S = _ptr(addvec), F, S
+    p.sum_out, p.ldsum = _ptr(sum_out), C if ldsum is None else ldsum
+    p.gamma, p.beta, p.eps = _ptr(gamma), _ptr(beta), eps
+    p.out, p.ldo = _ptr(out), C if ldo is None else ldo
+    call("ttvdm_layernorm", p)
+
+
+def im2col_s2(x, out, *, n_img, H, W, C) -> None:
+    call_raw("ttvdm_im2col_s2", c_void_p(_ptr(x)), c_void_p(_ptr(out)), n_img, H, W, C)
+
+
+def upsample2x(x, out, *, n_img, H, W, C) -> None:
+    call_raw("ttvdm_upsample2x", c_void_p(_ptr(x)), c_void_p(_ptr(out)), n_img, H, W, C)
+
+
+def axpy(a, b, out, scale: float, n: int) -> None:
+    call_raw("ttvdm_axpy", c_void_p(_ptr(a)), c_void_p(_ptr(b)), c_void_p(_ptr(out)), c_float(scale), c_size_t(n))
+
+
+def sampler_prepare(latents, image_latents, cond, model_in, *, c_pad, B_local, batch_offset, F, h, w, sigma) -> None:
+    p = PrepareParams()
+    p.latents, p.image_latents, p.cond = _ptr(latents), _ptr(image_latents), _ptr(cond)
+    p.model_in, p.c_pad = _ptr(model_in), c_pad
+    p.B_local, p.batch_offset, p.F, p.h, p.w, p.sigma = B_local, batch_offset, F, h, w, sigma
+    call("ttvdm_sampler_prepare", p)
+
+
+def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigma, sigma_next) -> None:
+    p = EulerParams()
+    p.latents, p.eps_u, p.eps_c, p.ld_eps = _ptr(latents), _ptr(eps_u), _ptr(eps_c), ld_eps
+    p.guidance, p.F, p.h, p.w, p.sigma, p.sigma_next = _ptr(guidance), F, h, w, sigma, sigma_next
+    call("ttvdm_sampler_euler_step", p)
