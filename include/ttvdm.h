@@ -44,7 +44,7 @@ uint64_t ttvdm_launch_count(void);
 /* ------------------------------------------------------------------------------------------------
  * K1/K2/K3/K4/K15 — one tcgen05 (TMA -> smem -> UMMA -> TMEM) GEMM family with fused epilogue.
  *
- *   out = s0 * (A (*) W^T + bias + rowvec[row / rows_per_vec]) + s1 * res1 + s2 * res2
+ *   out = act( s0 * (A (*) W^T + bias + rowvec[row / rows_per_vec]) + s1 * res1 + s2 * res2 )
  *
  * A-operand addressing modes (the implicit-GEMM part is done by TMA coordinates, never materialised):
  *   TTVDM_A_LINEAR : A = [M, k1] (optionally concatenated with a2 = [M, k2] along K)
@@ -75,13 +75,14 @@ typedef struct {
   const void* w;     /* bf16 [N, taps*(k1+k2)] */
   int M, N;          /* rows of the output, output features (before GEGLU halving) */
   const float* bias;   /* [N] or NULL */
-  const float* rowvec; /* [M / rows_per_vec, N] or NULL */
-  int rows_per_vec;
+  const float* rowvec; /* [M / rows_per_vec, ldrv] or NULL (timestep-embedding shift, one vector per video) */
+  int rows_per_vec; int ldrv;
   float s0;
   const void* res1; int ldr1; float s1; /* bf16 [M, *] or NULL */
   const void* res2; int ldr2; float s2;
   int geglu;
   void* out; int ldo; int out_fp32;     /* bf16 (default) or fp32 output, row stride ldo elements */
+  int act;                              /* 0 none, 1 SiLU (TimestepEmbedding MLPs) */
 } ttvdm_gemm_params;
 
 int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream);
@@ -178,6 +179,9 @@ int ttvdm_layernorm(const ttvdm_layernorm_params* p, void* stream);
  * ------------------------------------------------------------------------------------------------ */
 int ttvdm_im2col_s2(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
 int ttvdm_upsample2x(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
+/* K13 helper: out[i, :] = [cos(t_i * w_j) | sin(t_i * w_j)], w_j = exp(-ln(1e4) * j / (dim/2)) — diffusers
+ * Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0); t fp32 [n] on device, out bf16 [n, dim]. */
+int ttvdm_sinusoid(const float* t, void* out, int n, int dim, void* stream);
 /* out[r, :] = a[r, :] + scale * b[r, :]  (U4: ControlNet residual merge, svd/unet_spatio_temporal_condition.py:485-502) */
 int ttvdm_axpy(const void* a, const void* b, void* out, float scale, size_t n, void* stream);
 

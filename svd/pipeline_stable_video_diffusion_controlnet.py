@@ -1,0 +1,146 @@
+"""StableVideoDiffusionControlNetPipeline (VGL) — drop-in for svd/pipeline_stable_video_diffusion_controlnet.py.
+
+`__call__` keeps the reference's keyword arguments and defaults (:372-406). Steps 1-7 (CLIP / VAE / PIL handling)
+call the caller-supplied modules like the reference; step 8, the denoising loop (:623-720), runs on the fused
+sm_100a path. Differences that do not change results: `vae.encode(condition_img)` is hoisted out of the loop
+(:652 recomputes it every step; `.mode()` is deterministic), cross-attention K/V and timestep embeddings are
+precomputed, and the scheduler's unused per-step `randn` draw (diffusers Euler step with s_churn=0) is skipped.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from .pipeline_common import (PIL, StableVideoDiffusionPipelineOutput, SVDPipelineBase, _append_dims, randn_tensor)
+from .temporal_controlnet import ControlNetModel
+
+
+class StableVideoDiffusionControlNetPipeline(SVDPipelineBase):
+    @torch.no_grad()
+    def __call__(
+        self,
+        image=None,
+        condition_img: np.ndarray = None,
+        controlnet: ControlNetModel = None,
+        prompt=None,
+        use_text: bool = False,
+        text_encoder=None,
+        height: int = 576,
+        width: int = 1024,
+        num_frames: Optional[int] = None,
+        num_inference_steps: int = 25,
+        min_guidance_scale: float = 1.0,
+        max_guidance_scale: float = 3.0,
+        fps: int = 7,
+        motion_bucket_id: int = 127,
+        noise_aug_strength: float = 0.02,
+        decode_chunk_size: Optional[int] = None,
+        num_videos_per_prompt: Optional[int] = 1,
+        generator: Optional[Union[torch.Generator, List[torch.Generator]]] = None,
+        latents: Optional[torch.FloatTensor] = None,
+        output_type: Optional[str] = "pil",
+        callback_on_step_end: Optional[Callable[[int, int, Dict], None]] = None,
+        callback_on_step_end_tensor_inputs: List[str] = ["latents"],
+        return_dict: bool = True,
+        controlnet_conditioning_scale: Union[float, List[float]] = 1.0,
+        use_instructpix2pix: bool = False,
+        control_guidance_start: Union[float, List[float]] = 0.0,
+        control_guidance_end: Union[float, List[float]] = 1.0,
+        inner_conditioning_scale: float = 1.0,
+        guess_mode: bool = True,
+        image_guidance_scale: float = 7.5,
+        # --- additions for latent / benchmark mode: bypass CLIP and VAE
+        encoder_hidden_states: Optional[torch.Tensor] = None,
+        image_latents: Optional[torch.Tensor] = None,
+        controlnet_cond_latents: Optional[torch.Tensor] = None,
+    ):
+        if use_instructpix2pix:
+            raise NotImplementedError("use_instructpix2pix=True (3-way CFG) is not implemented; the shipped configs "
+                                      "use False (config/train_image2video_gesturenet.yaml:78)")
+        if controlnet is None:
+            raise ValueError("`controlnet` (GestureNet) is required by the VGL pipeline")
+        control_guidance_start, control_guidance_end = [control_guidance_start], [control_guidance_end]
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        num_frames = num_frames if num_frames is not None else self.unet.config.num_frames
+        decode_chunk_size = decode_chunk_size if decode_chunk_size is not None else num_frames
+        device = self._execution_device
+        do_cfg = max_guidance_scale > 1.0
+        if guess_mode and do_cfg:
+            raise NotImplementedError(
+                "guess_mode=True together with classifier-free guidance doubles the batch a second time in the "
+                "reference (:676-681) and is never used by its callers (config: inference_guess_mode False)")
+
+        latent_mode = encoder_hidden_states is not None
+        if latent_mode:
+            if image_latents is None or controlnet_cond_latents is None:
+                raise ValueError("latent mode needs encoder_hidden_states, image_latents and controlnet_cond_latents")
+            if height % 8 != 0 or width % 8 != 0:
+                raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+            ehs = encoder_hidden_states.to(device)
+            batch_size = ehs.shape[0] // (2 if do_cfg else 1)
+            img_lat = image_latents.to(device)
+            controlnet_cond = controlnet_cond_latents.to(device)
+        else:
+            self.check_inputs(image, height, width)
+            if PIL is not None and isinstance(image, PIL.Image.Image):
+                batch_size = 1
+            elif isinstance(image, list):
+                batch_size = len(image)
+            else:
+                batch_size = image.shape[0]
+            ehs = self.encode_clip(image, prompt, use_text, text_encoder, device, num_videos_per_prompt, do_cfg)
+            image_t = self._preprocess_image(image, height, width).to(device)
+            noise = randn_tensor(image_t.shape, generator=generator, device=image_t.device, dtype=image_t.dtype)
+            image_t = image_t + noise_aug_strength * noise
+            needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+            if needs_upcasting:
+                self.vae.to(dtype=torch.float32)
+            img_lat = self._encode_vae_image(image_t, device, num_videos_per_prompt, do_cfg).to(ehs.dtype)
+            cond_img = self.prepare_condition_image(condition_img, width, height, batch_size * num_videos_per_prompt,
+                                                    num_videos_per_prompt, device, controlnet.dtype, do_cfg, guess_mode)
+            # hoisted: the reference re-encodes this inside the loop on every step (:652)
+            controlnet_cond = self.vae.encode(cond_img.to(self.vae.dtype)).latent_dist.mode()
+            if needs_upcasting:
+                self.vae.to(dtype=torch.float16)
+        if batch_size * num_videos_per_prompt != 1:
+            raise ValueError("the VGL pipeline processes one video per call (reference limitation: controlnet_cond is "
+                             "[num_frames, ...] — svd/pipeline_stable_video_diffusion_controlnet.py:652-660)")
+
+        fps = fps - 1  # SVD was conditioned on fps - 1
+        added_time_ids = self._get_add_time_ids(fps, motion_bucket_id, noise_aug_strength, ehs.dtype, batch_size,
+                                                num_videos_per_prompt, do_cfg, guess_mode).to(device)
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        timesteps = self.scheduler.timesteps
+        num_channels_latents = self.unet.config.in_channels
+        latents = self.prepare_latents(batch_size * num_videos_per_prompt, num_frames, num_channels_latents, height,
+                                       width, ehs.dtype, device, generator, latents)
+        guidance_vec = torch.linspace(min_guidance_scale, max_guidance_scale, num_frames)
+        gs = guidance_vec.unsqueeze(0).to(device, latents.dtype).repeat(batch_size * num_videos_per_prompt, 1)
+        self._guidance_scale = _append_dims(gs, latents.ndim)
+
+        cond_scale = controlnet_conditioning_scale
+        if isinstance(cond_scale, list):
+            cond_scale = cond_scale[0]
+        n_t = len(timesteps)
+        keep = [1.0 - float(i / n_t < control_guidance_start[0] or (i + 1) / n_t > control_guidance_end[0])
+                for i in range(n_t)]
+        cond_scales = [cond_scale * k for k in keep]
+        self._num_timesteps = n_t
+
+        latents = self._denoise(latents, img_lat, ehs, added_time_ids, guidance_vec, num_frames, timesteps,
+                                controlnet=controlnet, controlnet_cond=controlnet_cond, cond_scales=cond_scales,
+                                callback_on_step_end=callback_on_step_end,
+                                callback_on_step_end_tensor_inputs=callback_on_step_end_tensor_inputs)
+
+        if not output_type == "latent":
+            frames = self.decode_latents(latents.to(self.vae.dtype), num_frames, decode_chunk_size)
+            frames = self._tensor2vid(frames, output_type=output_type)
+        else:
+            frames = latents
+        self.maybe_free_model_hooks()
+        if not return_dict:
+            return frames
+        return StableVideoDiffusionPipelineOutput(frames=frames)

@@ -1,0 +1,66 @@
+"""Shared builders for the parity tests: seeded tiny / SVD-config models and synthetic inputs."""
+from __future__ import annotations
+
+import torch
+
+from oracle import svd_oracle as O
+from svd.temporal_controlnet import ControlNetModel
+from svd.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+
+TINY = dict(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))
+SVD = dict(block_out_channels=(320, 640, 1280, 1280), num_attention_heads=(5, 10, 20, 20))
+
+
+def oracle_cfg(kind: dict) -> dict:
+    cfg = dict(O.SVD_CONFIG)
+    cfg.update(kind)
+    return cfg
+
+
+def randomize_special(model, seed: int) -> None:
+    """Zero-inits (GestureNet) get non-zero values and mix factors move off 0.5 so every path carries signal."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("mix_factor"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif name.startswith("controlnet_") or name.startswith("conv_in_concat"):
+                fan_in = p[0].numel() if p.ndim > 1 else p.numel()
+                p.copy_(torch.randn(p.shape, generator=g) * (fan_in ** -0.5 if p.ndim > 1 else 0.1))
+            elif ".norm" in name or name.startswith("conv_norm_out"):
+                if name.endswith("weight"):
+                    p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+                else:
+                    p.copy_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def build_models(kind: dict, seed: int = 1234, controlnet: bool = True):
+    torch.manual_seed(seed)
+    unet = UNetSpatioTemporalConditionModel(num_frames=14, **kind).eval()
+    randomize_special(unet, seed + 1)
+    cn = None
+    if controlnet:
+        cn = ControlNetModel(**kind).eval()
+        randomize_special(cn, seed + 2)
+    return unet, cn
+
+
+def state(model):
+    return {k: v.detach().float() for k, v in model.state_dict().items()}
+
+
+def make_inputs(B: int, F: int, h: int, w: int, L: int = 78, seed: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    sample = torch.randn(B, F, 8, h, w, generator=g)
+    ehs = torch.randn(B, L, 1024, generator=g)
+    ehs = torch.nn.functional.layer_norm(ehs, (L, 1024))
+    if B > 1:
+        ehs[0] = 0.0  # CFG: unconditional half is zeros
+    ati = torch.tensor([[6.0, 200.0, 0.1]] * B)
+    cond = torch.randn(F, 4, h, w, generator=g)
+    return sample, ehs, ati, cond
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))

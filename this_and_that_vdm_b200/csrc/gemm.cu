@@ -36,14 +36,14 @@ struct GemmArgs {
   // epilogue
   const float* bias;
   const float* rowvec;
-  int rows_per_vec;
+  int rows_per_vec, ldrv;
   float s0, s1, s2;
   const __nv_bfloat16* res1;
   const __nv_bfloat16* res2;
   int ldr1, ldr2;
   int geglu;
   void* out;
-  int ldo, out_fp32;
+  int ldo, out_fp32, act;
 };
 
 struct TileCoord {
@@ -174,6 +174,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         for (int i = 0; i < 32; ++i)
           if (col0 + i < g.N) a[i] += g.s2 * __bfloat162float(rp[i]);
       }
+    }
+    if (g.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] = a[i] / (1.f + __expf(-a[i]));
     }
     if (g.out_fp32) {
       float* o = reinterpret_cast<float*>(g.out) + out_row * g.ldo + col0;
@@ -339,7 +343,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         out_row = ((long long)t.img * g.H + t.h0) * g.W + s;
       }
       const float* rv = nullptr;
-      if (g.rowvec != nullptr && valid) rv = g.rowvec + (out_row / g.rows_per_vec) * g.N;
+      if (g.rowvec != nullptr && valid) rv = g.rowvec + (out_row / g.rows_per_vec) * g.ldrv;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -388,6 +392,9 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (p->geglu && (p->N % 2 != 0 || p->res1 || p->res2 || p->out_fp32))
     return fail(TTVDM_ERR_SHAPE, "gemm: geglu epilogue excludes residuals / fp32 out");
   if (p->rowvec && p->rows_per_vec <= 0) return fail(TTVDM_ERR_SHAPE, "gemm: rows_per_vec must be > 0");
+  if (p->rowvec && p->ldrv > 0 && (p->ldrv % 4 != 0 || (reinterpret_cast<uintptr_t>(p->rowvec) & 15)))
+    return fail(TTVDM_ERR_SHAPE, "gemm: rowvec must be 16 B aligned with ldrv %% 4 == 0");
+  if (p->act != 0 && p->act != 1) return fail(TTVDM_ERR_SHAPE, "gemm: unknown act %d", p->act);
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -468,6 +475,8 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   g.bias = p->bias;
   g.rowvec = p->rowvec;
   g.rows_per_vec = p->rows_per_vec > 0 ? p->rows_per_vec : 1;
+  g.ldrv = p->ldrv > 0 ? p->ldrv : p->N;
+  g.act = p->act;
   g.s0 = p->s0;
   g.s1 = p->s1;
   g.s2 = p->s2;

@@ -104,6 +104,17 @@ __global__ void euler_step_kernel(float* __restrict__ latents, const float* __re
   }
 }
 
+__global__ void sinusoid_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int n, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int row = i / half, j = i - row * half;
+  const float w = expf(-9.210340371976184f * (float)j / (float)half);
+  const float arg = t[row] * w;
+  out[(long long)row * dim + j] = __float2bfloat16(cosf(arg));
+  out[(long long)row * dim + half + j] = __float2bfloat16(sinf(arg));
+}
+
 static inline int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   const long long cap = (long long)g_num_sms * 16;
@@ -132,6 +143,16 @@ extern "C" int ttvdm_upsample2x(const void* x, void* out, int n_img, int H, int 
   upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, H, W, C / 8);
   TTVDM_CHECK_LAUNCH("upsample2x_kernel");
+  return 0;
+}
+
+extern "C" int ttvdm_sinusoid(const float* t, void* out, int n, int dim, void* stream_) {
+  if (int rc = ensure_init()) return rc;
+  if (!t || !out || n <= 0 || dim <= 0 || dim % 2 != 0) return fail(TTVDM_ERR_SHAPE, "sinusoid: n=%d dim=%d", n, dim);
+  const int total = n * (dim / 2);
+  sinusoid_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      t, static_cast<__nv_bfloat16*>(out), n, dim);
+  TTVDM_CHECK_LAUNCH("sinusoid_kernel");
   return 0;
 }
 

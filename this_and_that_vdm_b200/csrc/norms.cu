@@ -25,7 +25,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, in
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_inst);
-  if (threadIdx.x < 64) bins[threadIdx.x] = 0.f;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) bins[i] = 0.f;
   __syncthreads();
   for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
     float s = 0.f, ss = 0.f;
@@ -40,7 +40,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, in
     atomicAdd(&bins[grp * 2 + 1], ss);
   }
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&sums[inst * 64 + threadIdx.x], (double)bins[threadIdx.x]);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&sums[inst * 64 + i], (double)bins[i]);
 }
 
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, int ld1,

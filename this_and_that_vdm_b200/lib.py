@@ -24,10 +24,10 @@ class GemmParams(C.Structure):
         ("mode", c_int), ("a", c_void_p), ("a2", c_void_p), ("k1", c_int), ("k2", c_int),
         ("lda", c_int), ("lda2", c_int), ("n_img", c_int), ("H", c_int), ("W", c_int),
         ("w", c_void_p), ("M", c_int), ("N", c_int),
-        ("bias", c_void_p), ("rowvec", c_void_p), ("rows_per_vec", c_int), ("s0", c_float),
+        ("bias", c_void_p), ("rowvec", c_void_p), ("rows_per_vec", c_int), ("ldrv", c_int), ("s0", c_float),
         ("res1", c_void_p), ("ldr1", c_int), ("s1", c_float),
         ("res2", c_void_p), ("ldr2", c_int), ("s2", c_float),
-        ("geglu", c_int), ("out", c_void_p), ("ldo", c_int), ("out_fp32", c_int),
+        ("geglu", c_int), ("out", c_void_p), ("ldo", c_int), ("out_fp32", c_int), ("act", c_int),
     ]
 
 
@@ -96,7 +96,7 @@ class EulerParams(C.Structure):
 EXPORTS = [
     "ttvdm_init", "ttvdm_last_error", "ttvdm_abi_version", "ttvdm_launch_count",
     "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
-    "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy",
+    "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
     "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step",
 ]
 
@@ -163,10 +163,10 @@ def call_raw(name: str, *args) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int, k1: int,
          mode: int = A_LINEAR, lda: Optional[int] = None, a2: Optional[torch.Tensor] = None, k2: int = 0,
          lda2: int = 0, n_img: int = 0, H: int = 0, W: int = 0, bias: Optional[torch.Tensor] = None,
-         rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0, s0: float = 1.0,
+         rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0, ldrv: int = 0, s0: float = 1.0,
          res1: Optional[torch.Tensor] = None, ldr1: int = 0, s1: float = 1.0,
          res2: Optional[torch.Tensor] = None, ldr2: int = 0, s2: float = 1.0,
-         geglu: bool = False, ldo: Optional[int] = None, out_fp32: bool = False) -> None:
+         geglu: bool = False, ldo: Optional[int] = None, out_fp32: bool = False, act: int = 0) -> None:
     p = GemmParams()
     p.mode = mode
     p.a, p.a2, p.k1, p.k2 = _ptr(a), _ptr(a2), k1, k2
@@ -174,13 +174,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     p.lda2 = lda2 if lda2 else k2
     p.n_img, p.H, p.W = n_img, H, W
     p.w, p.M, p.N = _ptr(w), M, N
-    p.bias, p.rowvec, p.rows_per_vec, p.s0 = _ptr(bias), _ptr(rowvec), rows_per_vec, s0
+    p.bias, p.rowvec, p.rows_per_vec, p.ldrv, p.s0 = _ptr(bias), _ptr(rowvec), rows_per_vec, ldrv, s0
     p.res1, p.ldr1, p.s1 = _ptr(res1), ldr1 if ldr1 else N, s1
     p.res2, p.ldr2, p.s2 = _ptr(res2), ldr2 if ldr2 else N, s2
     p.geglu = int(geglu)
     p.out = _ptr(out)
     p.ldo = ldo if ldo is not None else (N // 2 if geglu else N)
     p.out_fp32 = int(out_fp32)
+    p.act = act
     call("ttvdm_gemm", p)
 
 
@@ -236,6 +237,10 @@ def im2col_s2(x, out, *, n_img, H, W, C) -> None:
 
 def upsample2x(x, out, *, n_img, H, W, C) -> None:
     call_raw("ttvdm_upsample2x", c_void_p(_ptr(x)), c_void_p(_ptr(out)), n_img, H, W, C)
+
+
+def sinusoid(t, out, *, n: int, dim: int) -> None:
+    call_raw("ttvdm_sinusoid", c_void_p(_ptr(t)), c_void_p(_ptr(out)), n, dim)
 
 
 def axpy(a, b, out, scale: float, n: int) -> None:

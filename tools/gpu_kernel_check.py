@@ -258,6 +258,7 @@ CASES = [
     ("attn_cross_temporal_oddS", lambda: case_attn_cross(B=2, F=2, S=135, temporal=True)),
     ("attn_temporal", lambda: case_attn_temporal()),
     ("groupnorm_4d", lambda: case_groupnorm()),
+    ("groupnorm_c64", lambda: case_groupnorm(n_inst=3, rows_per_inst=77, c1=64, silu=False)),
     ("groupnorm_concat", lambda: case_groupnorm(c1=1280, c2=640, silu=True)),
     ("groupnorm_5d_nosilu", lambda: case_groupnorm(n_inst=2, rows_per_inst=14 * 96, c1=640, silu=False, eps=1e-5)),
     ("layernorm_320", lambda: case_layernorm()),
