@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of 25-step VGL (UNet + GestureNet, CFG) generation on B200, the metric of BASELINE.json.
+
+A "step" of this bench is ONE VIDEO: a full 25-Euler-step VGL denoising of one 14-frame clip (CFG pair, B = 2)
+from synthetic latents with random-init weights — the hot path of
+svd/pipeline_stable_video_diffusion_controlnet.py:623-720. frames/s = n_gpus * 14 / seconds_per_video (weak
+scaling: every rank denoises its own video; one conditioning broadcast + one latent gather per round of videos).
+
+  value    : device-resident inputs, FusedDenoiser driven directly (hoists included), CUDA events, max over ranks
+  e2e      : the same videos through the public drop-in API (StableVideoDiffusionControlNetPipeline.__call__ in
+             latent mode) with pinned HOST inputs and a host read-back of the latents inside the timed region
+  roofline : tensor roofline of the dominant kernel family (gemm_kernel: all linear / conv3x3 / temporal conv),
+             from a CUDA-event pass over one Euler step; per-family shares of the step are reported beside it
+  cpu_baseline / --impl reference : the CPU fp32 oracle (oracle/svd_oracle.py — the reference's torch path
+             restated; diffusers is not installable here) timed on the host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FRAMES = 14
+NUM_STEPS = 25
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {"bf16_tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))),
+                    "bf16_tflops_burst": float(d.get("bf16_tflops", 0.0)),
+                    "hbm_gbs": float(d.get("hbm_gbs", 0.0)), "source": "measured (MEASURED_PEAKS.json, sustained)"}
+        except Exception:  # noqa: BLE001
+            pass
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md (sustained ~1.4 PF inside a long step; burst 1.59)
+    return {"bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md: ~1.4 PF sustained, 1.59 PF burst, 6.65 TB/s)"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_median": sorted(power)[len(power) // 2],
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_inputs(h: int, w: int, n_videos: int, seed: int = 0):
+    """BASELINE.md §4 synthetic inputs, generated on CPU in fp32 so every arm sees identical bits."""
+    from oracle_free_inputs import make  # local helper below (kept import-free of oracle/)
+    return make(h, w, n_videos, seed)
+
+
+def build_models(device):
+    from svd.temporal_controlnet import ControlNetModel
+    from svd.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    torch.manual_seed(1234)
+    unet = UNetSpatioTemporalConditionModel(num_attention_heads=(5, 10, 20, 20), num_frames=FRAMES).eval()
+    cn = ControlNetModel().eval()
+    g = torch.Generator().manual_seed(1236)
+    with torch.no_grad():  # GestureNet zero-inits -> non-zero (otherwise VGL == VL), mix factors as initialised
+        for name, p in cn.named_parameters():
+            if name.startswith("controlnet_") or name.startswith("conv_in_concat"):
+                fan_in = p[0].numel() if p.ndim > 1 else p.numel()
+                p.copy_(torch.randn(p.shape, generator=g) * (fan_in ** -0.5 if p.ndim > 1 else 0.1))
+    return unet.to(device), cn.to(device)
+
+
+# ====================================================================================================== our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from this_and_that_vdm_b200 import lib
+    from this_and_that_vdm_b200.sampler import FusedDenoiser
+    from svd.pipeline_stable_video_diffusion_controlnet import StableVideoDiffusionControlNetPipeline
+    from svd.scheduler import EulerDiscreteScheduler
+    from tools.flop_census import step_flops, step_flops_split
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.init(local_rank)
+    h, w = args.height // 8, args.width // 8
+    unet, cn = build_models(dev)
+    sched = EulerDiscreteScheduler()
+    sched.set_timesteps(NUM_STEPS)
+    sigmas, timesteps = sched.sigmas, sched.timesteps
+    guidance = torch.linspace(1.0, 3.0, FRAMES)
+    from this_and_that_vdm_b200.sharding import broadcast_conditioning, gather_latents
+
+    # one video per rank (weak scaling); rank 0 owns the conditioning of all videos of a round
+    cond_all = synth_inputs(h, w, world, seed=0) if rank == 0 else None
+    den = FusedDenoiser(unet._get_engine(), cn._get_engine())
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_video_resident(c) -> torch.Tensor:
+        idx = [rank, world + rank]
+        state = c["latents"][rank].clone().contiguous()
+        den.prepare(c["encoder_hidden_states"][idx], c["image_latents"][idx], c["added_time_ids"][idx], sigmas,
+                    timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][rank])
+        for i in range(NUM_STEPS):
+            den.step(i, state)
+        return state
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def round_resident():
+        if world > 1:
+            c = broadcast_conditioning(cond_dev if rank == 0 else None, dev)
+        else:
+            c = cond_dev
+        st = one_video_resident(c)
+        if world > 1:
+            gather_latents(st[None].contiguous())
+        return st
+
+    cond_dev = {k: v.to(dev) for k, v in cond_all.items()} if rank == 0 else None
+    for _ in range(args.warmup):
+        round_resident()
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between videos (the working set is >> L2 anyway)
+        round_resident()
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    launches = lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_video = ms / args.steps
+    value = world * FRAMES / (ms_per_video / 1e3)
+
+    # ---------------- e2e through the public pipeline API with pinned host buffers
+    pipe = StableVideoDiffusionControlNetPipeline.from_pretrained(None, unet=unet).to(dev)
+    host = synth_inputs(h, w, 1, seed=rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = torch.empty(1, FRAMES, 4, h, w, dtype=torch.float32).pin_memory()
+
+    def one_video_e2e():
+        res = pipe(controlnet=cn, height=args.height, width=args.width, num_frames=FRAMES,
+                   num_inference_steps=NUM_STEPS, min_guidance_scale=1.0, max_guidance_scale=3.0, fps=7,
+                   motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent", guess_mode=False,
+                   latents=host["latents"].to(dev, non_blocking=True) / sched.init_noise_sigma,
+                   encoder_hidden_states=host["encoder_hidden_states"].to(dev, non_blocking=True),
+                   image_latents=host["image_latents"].to(dev, non_blocking=True),
+                   controlnet_cond_latents=host["controlnet_cond"][0].to(dev, non_blocking=True))
+        out_host.copy_(res.frames, non_blocking=True)
+        torch.cuda.synchronize()
+
+    one_video_e2e()  # warm
+    sync()
+    n_e2e = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        one_video_e2e()
+    sync()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * FRAMES / e2e_s
+
+    # ---------------- roofline pass: CUDA events around every C-ABI call of ONE Euler step (rank 0)
+    roof = None
+    shares = None
+    if rank == 0:
+        peaks = load_peaks()
+        c = cond_dev
+        idx = [0, world]
+        state = c["latents"][0].clone().contiguous()
+        den.prepare(c["encoder_hidden_states"][idx], c["image_latents"][idx], c["added_time_ids"][idx], sigmas,
+                    timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][0])
+        den.step(0, state)
+        torch.cuda.synchronize()
+        lib.start_profile()
+        den.step(1, state)
+        rec = lib.stop_profile()
+        fam = {}
+        for name, info, ms_k in rec:
+            f = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            f["ms"] += ms_k; f["flops"] += info.get("flops", 0.0); f["launches"] += 1
+        tot_ms = sum(f["ms"] for f in fam.values())
+        shares = {k.replace("ttvdm_", ""): {"share": round(v["ms"] / tot_ms, 4), "ms": round(v["ms"], 3),
+                                             "launches": v["launches"],
+                                             "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None}
+                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        gemm_alg, attn_alg, _ = step_flops_split(h, w, 2, True)
+        g = fam.get("ttvdm_gemm", {"ms": 1.0, "launches": 1})
+        achieved = gemm_alg / g["launches"] / (g["ms"] / g["launches"]) / 1e9  # TFLOP/s: alg flops per launch / avg ms
+        roof = {"kernel": "gemm_kernel (linear + conv3x3 + temporal-conv family)", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["bf16_tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
+                "algorithmic_tflop_per_step": round(gemm_alg / 1e12, 3),
+                "whole_step": {"algorithmic_tflop": round(step_flops(h, w, 2, True) / 1e12, 3),
+                               "achieved_tflops": round(step_flops(h, w, 2, True) * NUM_STEPS / (ms_per_video / 1e3) / 1e12, 1),
+                               "frac": round(step_flops(h, w, 2, True) * NUM_STEPS / (ms_per_video / 1e3) / 1e12 / peaks["bf16_tflops"], 4)},
+                "attention": {"algorithmic_tflop_per_step": round(attn_alg / 1e12, 3),
+                              "achieved_tflops": round(attn_alg / (fam.get("ttvdm_attn_spatial", {"ms": 1})["ms"] + fam.get("ttvdm_attn_cross", {"ms": 0})["ms"]) / 1e9, 1)}}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(args, sample_only=True)
+
+    if rank == 0:
+        line = {
+            "metric": "frames/sec for 14-frame 576x1024 VGL, 25 Euler steps" if (args.height, args.width) == (576, 1024)
+            else f"frames/sec for 14-frame {args.height}x{args.width} VGL, 25 Euler steps",
+            "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_video, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (random-init weights, seeded N(0,1) latents/conditioning)",
+            "config": {"workload": f"VGL (UNet+GestureNet) 25-step Euler, 14x{args.height}x{args.width}, CFG pair (B=2) per video, "
+                                   f"one video per GPU", "step": "one video = 25 Euler steps", "latent": [FRAMES, 4, h, w],
+                       "parallelism": f"dp{world} (whole CFG pairs per rank; 1 conditioning broadcast + 1 latent gather per round)",
+                       "l2": "192 MB flush write between videos; per-step working set >> 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 4), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4), "api": "StableVideoDiffusionControlNetPipeline.__call__ (latent mode)",
+                    "videos_timed": n_e2e},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_shares": shares,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ====================================================================================================== reference arm
+def cpu_reference(args, sample_only: bool = False, steps: int = 1, warmup: int = 0):
+    """The reference's CPU path = the fp32 oracle on all host threads. Bounded sample: ONE VGL Euler step (GestureNet +
+    UNet forward, CFG pair) at 14x256x384 (latent 32x48, BASELINE.json configs[0] size), extrapolated to the bench
+    workload by the algorithmic FLOP ratio (tools/flop_census.py)."""
+    from oracle import svd_oracle as O
+    from tools.flop_census import step_flops
+    torch.set_num_threads(os.cpu_count() or 1)
+    h, w = args.height // 8, args.width // 8
+    sh, sw = min(h, 32), min(w, 48)
+    unet, cn = build_models("cpu")
+    usd = {k: v.detach() for k, v in unet.state_dict().items()}
+    csd = {k: v.detach() for k, v in cn.state_dict().items()}
+    c = synth_inputs(sh, sw, 1, seed=0)
+    cfg = dict(O.SVD_CONFIG)
+    sig = O.karras_sigmas(NUM_STEPS)
+    img = c["image_latents"][:, None].repeat(1, FRAMES, 1, 1, 1)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.denoise_loop(usd, cfg, c["latents"], img, c["encoder_hidden_states"], c["added_time_ids"], NUM_STEPS, 1.0,
+                           3.0, csd, cfg, c["controlnet_cond"][0], 1.0, max_steps=1)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    t_step = sum(times) / len(times)
+    scale = step_flops(h, w, 2, True) / step_flops(sh, sw, 2, True)
+    video_s = t_step * scale * NUM_STEPS
+    return {"value": round(FRAMES / video_s, 6), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 VGL Euler step (GestureNet+UNet fp32, CFG pair) at 14x{sh * 8}x{sw * 8} = {t_step:.2f} s on "
+                      f"{torch.get_num_threads()} threads; extrapolated x{scale:.2f} (algorithmic FLOPs) x25 steps to "
+                      f"14x{args.height}x{args.width}",
+            "sample_seconds": round(t_step, 3), "sample_tflops": round(step_flops(sh, sw, 2, True) / t_step / 1e12, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu = cpu_reference(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    line = {"impl": "reference",
+            "metric": "frames/sec for 14-frame 576x1024 VGL, 25 Euler steps" if (args.height, args.width) == (576, 1024)
+            else f"frames/sec for 14-frame {args.height}x{args.width} VGL, 25 Euler steps",
+            "value": cpu["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(FRAMES / cpu["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (same seeds as the sm_100a arm)",
+            "config": {"workload": f"VGL (UNet+GestureNet) 25-step Euler, 14x{args.height}x{args.width}, CFG pair (B=2) per video",
+                       "note": "reference CPU PyTorch path restated (oracle, diffusers not installable); bounded sample, extrapolated"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--height", type=int, default=576)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,12 +151,57 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+# Optional per-call CUDA-event timing (bench.py's roofline pass): records (entry point, params, start, end).
+_profile: Optional[list] = None
+
+
+def start_profile() -> None:
+    global _profile
+    _profile = []
+
+
+def stop_profile() -> list:
+    """Returns [(name, info dict, milliseconds)] for every call since start_profile(); synchronises once."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    return [(n, info, e0.elapsed_time(e1)) for (n, info, e0, e1) in rec]
+
+
+def _info(name: str, p) -> dict:
+    if name == "ttvdm_gemm":
+        taps = 9 if p.mode == A_CONV3X3 else (3 if p.mode == A_TCONV3 else 1)
+        return {"flops": 2.0 * p.M * p.N * taps * (p.k1 + (p.k2 if p.a2 else 0)), "mode": p.mode, "M": p.M, "N": p.N,
+                "K": taps * (p.k1 + (p.k2 if p.a2 else 0))}
+    if name == "ttvdm_attn_spatial":
+        return {"flops": 4.0 * p.n_img * p.heads * p.seq * p.seq * 64}
+    if name == "ttvdm_attn_cross":
+        return {"flops": 4.0 * p.rows * p.heads * p.L * 64}
+    if name == "ttvdm_attn_temporal":
+        return {"flops": 4.0 * p.B * p.S * p.heads * p.F * p.F * 64}
+    return {"flops": 0.0}
+
+
 def call(name: str, params: C.Structure) -> None:
+    if _profile is None:
+        _check(getattr(load(), name)(C.byref(params), _stream()), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _check(getattr(load(), name)(C.byref(params), _stream()), name)
+    e1.record()
+    _profile.append((name, _info(name, params), e0, e1))
 
 
 def call_raw(name: str, *args) -> None:
+    if _profile is None:
+        _check(getattr(load(), name)(*args, _stream()), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     _check(getattr(load(), name)(*args, _stream()), name)
+    e1.record()
+    _profile.append((name, {"flops": 0.0}, e0, e1))
 
 
 # ------------------------------------------------------------------------------------------------ wrappers
