@@ -172,6 +172,20 @@ def run_ours(args):
         return st
 
     cond_dev = {k: v.to(dev) for k, v in cond_all.items()} if rank == 0 else None
+    if args.profile_only:
+        # ncu helper: `ncu --profile-from-start off ... python bench.py --profile-only` captures exactly ONE Euler step
+        c = cond_dev
+        state = c["latents"][0].clone().contiguous()
+        den.prepare(c["encoder_hidden_states"][[0, world]], c["image_latents"][[0, world]], c["added_time_ids"][[0, world]],
+                    sigmas, timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][0])
+        den.step(0, state)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        den.step(1, state)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_only": True, "launches_in_range": "one VGL Euler step"}))
+        return
     for _ in range(args.warmup):
         round_resident()
     sync()
@@ -357,6 +371,7 @@ def main():
     ap.add_argument("--height", type=int, default=576)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="run prepare + 2 Euler steps; cudaProfilerStart/Stop around the 2nd")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

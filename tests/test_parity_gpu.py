@@ -1,0 +1,225 @@
+"""Whole-path parity on the B200: the sm_100a engine (bf16 storage / fp32 accumulate) against the CPU fp32 oracle on
+the same seeded inputs, through the reference-facing API (svd.* forward / pipeline __call__).
+
+Tolerance (SURVEY.md §7 'Tolerance definition'): rel-L2 over the tensor vs the fp32 oracle; the north star's
+"1e-3 relative bf16 tolerance" is read as  err(engine) <= err(torch-eager bf16 of the same graph) + 1e-3, with the
+eager-bf16 error measured in the same test (oracle functions on CUDA bf16 tensors), plus an absolute cap of 3e-2."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import svd_oracle as O
+from tests.common import SVD, TINY, build_models, make_inputs, oracle_cfg, rel_l2, state
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+CAP = 3e-2
+T0 = torch.tensor(1.63777)
+
+
+def _eager_bf16(fn, sds, *tensors, **kw):
+    dev = "cuda"
+    sds = [{k: v.to(dev, torch.bfloat16) for k, v in sd.items()} for sd in sds]
+    ts = [t.to(dev, torch.bfloat16) if (torch.is_tensor(t) and t.is_floating_point() and t.ndim > 0) else
+          (t.to(dev) if torch.is_tensor(t) else t) for t in tensors]
+    return fn(sds, *ts, **kw)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    unet, cn = build_models(TINY)
+    usd, csd = state(unet), state(cn)
+    unet.to("cuda")
+    cn.to("cuda")
+    return unet, cn, usd, csd, oracle_cfg(TINY)
+
+
+def test_unet_forward_vs_oracle_and_golden(tiny):
+    unet, cn, usd, csd, cfg = tiny
+    sample, ehs, ati, cond = make_inputs(2, 14, 16, 24)
+    with torch.no_grad():
+        ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
+        eager = _eager_bf16(lambda s, *a: O.unet_forward(s[0], cfg, *a), [usd], sample, T0, ehs, ati)
+        out = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
+    e, ee = rel_l2(out, ref), rel_l2(eager, ref)
+    assert out.shape == (2, 14, 4, 16, 24) and out.dtype == torch.float32
+    assert e <= ee + 1e-3 and e < CAP, (e, ee)
+    gold = torch.load(GOLD / "tiny_vgl.pt")
+    assert rel_l2(out, gold["unet_vl"]) < CAP
+
+
+def test_controlnet_and_residual_merge_vs_oracle(tiny):
+    unet, cn, usd, csd, cfg = tiny
+    sample, ehs, ati, cond = make_inputs(2, 14, 16, 24)
+    cc = torch.cat([cond, cond])
+    with torch.no_grad():
+        d_ref, m_ref = O.controlnet_forward(csd, cfg, sample, T0, ehs, ati, cc, 0.8)
+        y_ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati, d_ref, m_ref)
+        d, m = cn(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), controlnet_cond=cc.cuda(), conditioning_scale=0.8,
+                  return_dict=False)
+        y = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), down_block_additional_residuals=d,
+                 mid_block_additional_residual=m, return_dict=False)[0]
+        d_e, m_e = _eager_bf16(lambda s, *a: O.controlnet_forward(s[0], cfg, *a), [csd], sample, T0, ehs, ati, cc, 0.8)
+    assert len(d) == 12 and all(a.shape == b.shape for a, b in zip(d, d_ref)) and m.shape == m_ref.shape
+    assert rel_l2(m, m_ref) <= rel_l2(m_e, m_ref) + 1e-3
+    for a, b, c in zip(d, d_ref, d_e):
+        assert rel_l2(a, b) <= rel_l2(c, b) + 1e-3
+    assert rel_l2(y, y_ref) < CAP
+    gold = torch.load(GOLD / "tiny_vgl.pt")
+    d1, m1 = cn(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), controlnet_cond=cc.cuda(), return_dict=False)
+    assert rel_l2(m1, gold["cn_mid"]) < CAP and rel_l2(d1[11], gold["cn_down11"]) < CAP
+
+
+def test_guess_mode_scales_and_timestep_forms(tiny):
+    unet, cn, usd, csd, cfg = tiny
+    sample, ehs, ati, cond = make_inputs(1, 14, 8, 8)
+    with torch.no_grad():
+        d_ref, m_ref = O.controlnet_forward(csd, cfg, sample, 0.5, ehs, ati, cond, 1.0, guess_mode=True)
+        d, m = cn(sample.cuda(), 0.5, ehs.cuda(), ati.cuda(), controlnet_cond=cond.cuda(), guess_mode=True,
+                  return_dict=False)
+        a = unet(sample.cuda(), 0.5, ehs.cuda(), ati.cuda()).sample                      # python float
+        b = unet(sample.cuda(), torch.tensor([0.5]).cuda(), ehs.cuda(), ati.cuda()).sample  # 1-dim tensor
+    assert rel_l2(d[0], d_ref[0]) < CAP and rel_l2(m, m_ref) < CAP
+    assert torch.equal(a, b)
+
+
+def test_zero_init_gesturenet_equals_vl_on_gpu(tiny):
+    """§8c item 3 on the CUDA path: zero-initialised GestureNet => VGL == VL bit for bit."""
+    from svd.temporal_controlnet import ControlNetModel
+    unet = tiny[0]
+    cn0 = ControlNetModel(**TINY).to("cuda")
+    sample, ehs, ati, cond = make_inputs(2, 14, 8, 16)
+    with torch.no_grad():
+        d, m = cn0(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), controlnet_cond=torch.cat([cond, cond]).cuda(),
+                   return_dict=False)
+        assert all(float(x.abs().max()) == 0 for x in d) and float(m.abs().max()) == 0
+        y0 = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
+        y1 = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), down_block_additional_residuals=d,
+                  mid_block_additional_residual=m).sample
+    assert torch.equal(y0, y1)
+
+
+def test_temporal_context_quirk_on_gpu(tiny):
+    """Changing context 0 must change batch element 1 only through its EVEN pixels' temporal cross-attention."""
+    unet = tiny[0]
+    eng = unet._get_engine()
+    t = eng.down[0]["tf"][0]
+    B, F, h, w = 2, 14, 4, 4
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B * F * h * w, t.C, generator=g).to("cuda", torch.bfloat16)
+    ehs = torch.randn(B, 6, 1024, generator=g)
+    ehs2 = ehs.clone()
+    ehs2[0] = ehs[1]
+    eng._ensure_pos_emb(F)
+    outs = []
+    for e in (ehs, ehs2):
+        kv = eng.context_kv(e.cuda())
+        outs.append(eng._transformer(t, x.clone(), kv[0], B=B, F=F, H=h, W=w, n_ctx=B, batch_offset=0).float())
+    torch.cuda.synchronize()
+    d = (outs[0] - outs[1]).view(B, F, h * w, t.C)[1].abs().amax(dim=(0, 2))  # per pixel of batch element 1
+    rows = torch.arange(h * w) + h * w
+    even = (rows % 2 == 0).cuda()
+    assert float(d[even].min()) > 0 and float(d[~even].max()) == 0.0
+
+
+def test_sharded_halves_equal_whole_pair(tiny):
+    """Batch sharding (§8e): running the uncond / cond halves separately (b_local=1, global row indices for the
+    context quirk) reproduces the whole-pair noise prediction (up to the order of the fp64 GroupNorm atomics)."""
+    from this_and_that_vdm_b200.sampler import FusedDenoiser
+    unet, cn = tiny[0], tiny[1]
+    F, h, w = 14, 8, 16
+    sample, ehs, ati, cond = make_inputs(2, F, h, w)
+    sig = O.karras_sigmas(25)
+    ts = O.euler_timesteps(sig)
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(1, 4, h, w, generator=g)
+    img2 = torch.cat([torch.zeros_like(img), img]).cuda()
+    lat = (torch.randn(F, 4, h, w, generator=g) * 20).cuda()
+    args = (ehs.cuda(), img2, ati.cuda(), sig, ts, torch.linspace(1, 3, F))
+    kw = dict(num_frames=F, height=h, width=w, controlnet_cond=cond.cuda())
+    den = FusedDenoiser(unet._get_engine(), cn._get_engine())
+    den.prepare(*args, **kw)
+    whole = den.predict(10, lat).clone()
+    rows = F * h * w
+    for off in (0, 1):
+        den.prepare(*args, batch_offset=off, b_local=1, **kw)
+        half = den.predict(10, lat)
+        assert rel_l2(half, whole[off * rows:(off + 1) * rows]) < 1e-3, off
+
+
+def test_pipeline_25_steps_vs_oracle_loop(tiny):
+    """Config-3 shape of BASELINE.json at tiny width: the full 25-step VGL loop through the drop-in pipeline API."""
+    from svd.pipeline_stable_video_diffusion_controlnet import StableVideoDiffusionControlNetPipeline
+    unet, cn, usd, csd, cfg = tiny
+    F, h, w = 14, 8, 16
+    sample, ehs, ati, cond = make_inputs(2, F, h, w)
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(1, F, 4, h, w, generator=g)
+    img = torch.randn(1, 4, h, w, generator=g)
+    img2 = torch.cat([torch.zeros_like(img), img])
+    sig = O.karras_sigmas(25)
+    with torch.no_grad():
+        ref = O.denoise_loop(usd, cfg, noise * O.init_noise_sigma(sig), img2[:, None].repeat(1, F, 1, 1, 1), ehs, ati, 25,
+                             1.0, 3.0, csd, cfg, cond, 1.0)
+    pipe = StableVideoDiffusionControlNetPipeline.from_pretrained("unused", unet=unet).to("cuda")
+    seen = []
+    res = pipe(controlnet=cn, height=h * 8, width=w * 8, num_frames=F, num_inference_steps=25, max_guidance_scale=3.0,
+               fps=7, motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent", guess_mode=False,
+               latents=noise.cuda(), encoder_hidden_states=ehs.cuda(), image_latents=img2.cuda(),
+               controlnet_cond_latents=cond.cuda(),
+               callback_on_step_end=lambda p, i, t, kw: seen.append(i) or {})
+    out = res.frames
+    assert out.shape == (1, F, 4, h, w) and seen == list(range(25))
+    e = rel_l2(out, ref)
+    assert e < 5e-2, e   # 25 compounding bf16 steps; see DESIGN.md for the measured value
+
+
+def test_vl_pipeline_two_videos_latent_mode(tiny):
+    from svd.pipeline_stable_video_diffusion import StableVideoDiffusionPipeline
+    unet, _, usd, _, cfg = tiny
+    F, h, w = 14, 8, 8
+    g = torch.Generator().manual_seed(2)
+    ehs1 = torch.randn(2, 78, 1024, generator=g)
+    ehs = torch.cat([torch.zeros_like(ehs1), ehs1])
+    img = torch.randn(2, 4, h, w, generator=g)
+    img2 = torch.cat([torch.zeros_like(img), img])
+    noise = torch.randn(2, F, 4, h, w, generator=g)
+    ati = torch.tensor([[6.0, 127.0, 0.02]] * 2)
+    sig = O.karras_sigmas(3)
+    pipe = StableVideoDiffusionPipeline.from_pretrained("unused", unet=unet).to("cuda")
+    out = pipe(height=h * 8, width=w * 8, num_frames=F, num_inference_steps=3, output_type="latent", latents=noise.cuda(),
+               encoder_hidden_states=ehs.cuda(), image_latents=img2.cuda()).frames
+    assert out.shape == (2, F, 4, h, w)
+    # each video is an independent CFG pair: compare video 1 against the oracle loop run on its own pair
+    with torch.no_grad():
+        lat = noise[1:2] * (700.0 ** 2 + 1) ** 0.5
+        sigs = torch.cat([(700.0 ** (1 / 7) + torch.linspace(0, 1, 3, dtype=torch.float64) * (0.002 ** (1 / 7) - 700.0 ** (1 / 7))) ** 7,
+                          torch.zeros(1, dtype=torch.float64)]).float()
+        tsx = 0.25 * torch.log(sigs[:-1])
+        gd = torch.linspace(1, 3, F)[None, :, None, None, None]
+        pair_e, pair_i = ehs[[1, 3]], img2[[1, 3]][:, None].repeat(1, F, 1, 1, 1)
+        for i in range(3):
+            s, sn = float(sigs[i]), float(sigs[i + 1])
+            x = torch.cat([torch.cat([lat] * 2) / (s * s + 1) ** 0.5, pair_i], dim=2)
+            eps = O.unet_forward(usd, cfg, x, tsx[i], pair_e, ati)
+            eu, ec = eps.chunk(2)
+            lat = O.euler_step(eu + gd * (ec - eu), lat, s, sn)
+    assert rel_l2(out[1:2], lat) < 3e-2
+
+
+@pytest.mark.slow
+def test_svd_config_forward_vs_oracle():
+    """BASELINE.json configs[0]: single UNet forward, SVD config, 14x32x48 latent, B = 1 — numerics vs the oracle."""
+    unet, _ = build_models(SVD, controlnet=False)
+    usd, cfg = state(unet), oracle_cfg(SVD)
+    sample, ehs, ati, _ = make_inputs(1, 14, 32, 48)
+    ehs = ehs + 0  # B = 1: conditional context
+    with torch.no_grad():
+        ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
+        unet.to("cuda")
+        out = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
+        eager = _eager_bf16(lambda s, *a: O.unet_forward(s[0], cfg, *a), [usd], sample, T0, ehs, ati)
+    e, ee = rel_l2(out, ref), rel_l2(eager, ref)
+    assert e <= ee + 1e-3 and e < CAP, (e, ee)

@@ -170,10 +170,9 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   const int n_inst = p->rows / p->rows_per_inst;
   const int threads = gn_threads(C / 2);
   if (threads == 0) return fail(TTVDM_ERR_SHAPE, "groupnorm: unsupported C=%d", C);
-  // ~8 CTAs per SM worth of row chunks
-  int rows_per_cta = (int)(((long long)p->rows + g_num_sms * 8 - 1) / (g_num_sms * 8));
-  if (rows_per_cta < 8) rows_per_cta = 8;
-  if (rows_per_cta > 256) rows_per_cta = 256;
+  // fixed chunk => the fp32 partial sums (and therefore the statistics) do not depend on how many sequences this
+  // rank holds: a sharded half-pair reproduces the whole-pair result
+  const int rows_per_cta = 32;
   const int chunks = (p->rows_per_inst + rows_per_cta - 1) / rows_per_cta;
   cudaError_t e = cudaMemsetAsync(p->stats, 0, (size_t)n_inst * 64 * sizeof(double), stream);
   if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "groupnorm: memset: %s", cudaGetErrorString(e));
