@@ -262,6 +262,14 @@ def run_ours(args):
         for name, info, ms_k in rec:
             f = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
             f["ms"] += ms_k; f["flops"] += info.get("flops", 0.0); f["launches"] += 1
+        shp = {}
+        for name, info, ms_k in rec:
+            if name == "ttvdm_gemm":
+                k = (info["mode"], info["M"], info["N"], info["K"])
+                d = shp.setdefault(k, [0.0, 0.0, 0])
+                d[0] += ms_k; d[1] += info["flops"]; d[2] += 1
+        gemm_shapes = [{"mode": k[0], "M": k[1], "N": k[2], "K": k[3], "n": v[2], "ms": round(v[0], 3),
+                        "tflops": round(v[1] / v[0] / 1e9, 1)} for k, v in sorted(shp.items(), key=lambda kv: -kv[1][0])[:14]]
         tot_ms = sum(f["ms"] for f in fam.values())
         shares = {k.replace("ttvdm_", ""): {"share": round(v["ms"] / tot_ms, 4), "ms": round(v["ms"], 3),
                                              "launches": v["launches"],
@@ -301,9 +309,15 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "api": "StableVideoDiffusionControlNetPipeline.__call__ (latent mode)",
                     "videos_timed": n_e2e},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_shares": shares,
+            "gemm_shapes": gemm_shapes if rank == 0 else None,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+        try:
+            (ROOT / "gpurun_out").mkdir(exist_ok=True)
+            (ROOT / "gpurun_out" / f"bench_last_{args.height}x{args.width}_n{world}.json").write_text(json.dumps(line, indent=1))
+        except Exception:  # noqa: BLE001
+            pass
     if world > 1:
         dist.destroy_process_group()
 

@@ -3,9 +3,9 @@
 //   S = Q K^T   : tcgen05.mma M=128 N=128 K=64, Q/K tiles staged by TMA (128B swizzle), S in TMEM cols [0,128)
 //   softmax     : 128 threads (one query row each) read S with tcgen05.ld, online max/sum in fp32 registers,
 //                 write P (bf16) into a 128B-swizzled K-major smem tile
-//   O_j = P V   : tcgen05.mma M=128 N=64 K=128, V tile used in place as the MN-major B operand, O_j in TMEM
-//                 cols [128,192); the softmax threads fold O_j into their fp32 register accumulator with the
-//                 usual exp2(m_old - m_new) rescale, so no TMEM read-modify-write is needed.
+//   O += P V    : tcgen05.mma M=128 N=64 K=128, V tile used in place as the MN-major B operand, O accumulates in TMEM
+//                 cols [128,192) across KV tiles; the reference max is only moved when it grows by more than 2^8
+//                 (lazy rescale), in which case the softmax warps scale their O rows in TMEM (tcgen05.ld/st).
 //
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..7: softmax / epilogue
 //
@@ -166,7 +166,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int k = 0; k < 8; ++k) {
           const uint64_t p_desc = make_sdesc_sw128(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024);
           const uint64_t v_desc = make_sdesc_sw128(sv + k * 2048, 16, 1024);
-          tc_mma_ss(tmem_O, p_desc, v_desc, idesc_pv, k != 0);
+          tc_mma_ss(tmem_O, p_desc, v_desc, idesc_pv, (j | k) != 0);  // O accumulates across KV tiles
         }
         tc_commit(&v_empty[st]);
         tc_commit(o_done);
@@ -192,10 +192,6 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-    float o_acc[kD];
-#pragma unroll
-    for (int d = 0; d < kD; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
     int my_ctx = -1;
     if (g.kv_mode == KV_CROSS_TEMPORAL) {
       // global row -> (b, f, s); temporal batch row (b, s) reads context (b*S + s) mod n_ctx  [reference quirk]
@@ -204,94 +200,129 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int b = (int)(row / ((long long)g.F * g.S)) + g.batch_offset;
       my_ctx = (int)(((long long)b * g.S + s) % g.n_ctx);
     }
+    const float c2 = g.scale_log2;
+    float m_used = -INFINITY;  // (stale) row max the exponentials are taken against
+    float l_run = 0.f;
+    uint8_t* const prow0 = sP + r * 128;
+    const int rx = r & 7;
     for (int j = 0; j < n_kv_tiles; ++j) {
-      int kv_valid;
+      int kv_valid = kKT;
       if (g.kv_mode == KV_SELF) kv_valid = min(kKT, g.seq_kv - j * kKT);
       else kv_valid = g.seq_kv;
       const bool row_off = (g.kv_mode == KV_CROSS_TEMPORAL) && (my_ctx != j);
+      const bool masked = (kv_valid < kKT) || (g.kv_mode == KV_CROSS_TEMPORAL);  // CTA-uniform
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // ---- pass 1: row max of this tile
       float mx = -INFINITY;
+      if (!masked) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      if (row_off) mx = -INFINITY;
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2((m_run - m_use) * g.scale_log2);  // m_run = -inf -> 0
-      if (j > 0) {
-        // fold the previous tile's O_{j-1} = P_{j-1} V_{j-1} (also guarantees P smem is free again)
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+          tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        if (row_off) mx = -INFINITY;
+      }
+      // ---- lazy rescale: only move the reference max when it grows by more than 2^8 (exp2 domain)
+      const bool grow = (mx - m_used) * c2 > 8.0f;  // j == 0: m_used = -inf -> true (NaN if both -inf -> false)
+      const float m_new = grow ? mx : m_used;
+      if (j > 0) {
+        // O_{0..j-1} has been accumulated in TMEM; PV_{j-1} must be complete before O is touched / P is overwritten
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? ex2((m_used - m_new) * c2) : 1.0f;  // m_used = -inf -> 0 (row still empty)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32(tmem_O + lane_addr + c * 32, v);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
         }
       }
-      // pass 2: probabilities -> swizzled smem (bf16), row sum
-      float sum = 0.f;
-      const float m_s = m_use * g.scale_log2;
+      m_used = m_new;
+      const float ms = (m_used == -INFINITY) ? 0.f : m_used * c2;
+      // ---- pass 2: probabilities -> 128B-swizzled smem tile (bf16), row sum
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_S + lane_addr + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (!masked) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(__uint_as_float(v[i]) * g.scale_log2 - m_s);
-          float p1 = ex2(__uint_as_float(v[i + 1]) * g.scale_log2 - m_s);
-          if (row_off || c * 32 + i >= kv_valid) p0 = 0.f;
-          if (row_off || c * 32 + i + 1 >= kv_valid) p1 = 0.f;
-          pk[i >> 1] = pack_bf16(p0, p1);
-          // accumulate the sum of what the tensor core will actually see (bf16-rounded)
-          const float2 pr = unpack_bf16(pk[i >> 1]);
-          sum += pr.x + pr.y;
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[i]), c2, -ms));
+            const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), c2, -ms));
+            sum0 += p0;
+            sum1 += p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2(fmaf(__uint_as_float(v[i]), c2, -ms));
+            float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), c2, -ms));
+            if (row_off || c * 32 + i >= kv_valid) p0 = 0.f;
+            if (row_off || c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+            sum0 += p0;
+            sum1 += p1;
+            pk[i >> 1] = pack_bf16(p0, p1);
+          }
         }
         // keys [c*32, c*32+32) live in K-block (c>>1), 16-byte chunks ((c&1)*4 .. +3), XOR-swizzled by (row & 7)
-        uint8_t* prow = sP + (c >> 1) * kTileBytes + r * 128;
+        uint8_t* prow = prow0 + (c >> 1) * kTileBytes;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c & 1) * 4 + ch) ^ (r & 7);
+          const int chunk = ((c & 1) * 4 + ch) ^ rx;
           *reinterpret_cast<uint4*>(prow + chunk * 16) =
               make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
+      l_run += sum0 + sum1;
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
     }
-    // last tile's O
+    // ---- epilogue: O / l
     mbar_wait(o_done, (n_kv_tiles - 1) & 1);
     tc_fence_after();
     const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+    __nv_bfloat16* orow = g.out + (long long)(q_row0 + r) * g.ldo + head * kD;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_O + lane_addr + c * 32, v);
       tmem_ld_wait();
+      if (r < q_valid) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(v[i])) * inv;
-    }
-    if (r < q_valid) {
-      uint4* op = reinterpret_cast<uint4*>(g.out + (long long)(q_row0 + r) * g.ldo + head * kD);
+        for (int i = 0; i < 4; ++i) {
+          uint32_t w4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        op[i] = make_uint4(pack_bf16(o_acc[i * 8], o_acc[i * 8 + 1]), pack_bf16(o_acc[i * 8 + 2], o_acc[i * 8 + 3]),
-                           pack_bf16(o_acc[i * 8 + 4], o_acc[i * 8 + 5]), pack_bf16(o_acc[i * 8 + 6], o_acc[i * 8 + 7]));
+          for (int k2 = 0; k2 < 4; ++k2)
+            w4[k2] = pack_bf16(__uint_as_float(v[i * 8 + k2 * 2]) * inv, __uint_as_float(v[i * 8 + k2 * 2 + 1]) * inv);
+          *(reinterpret_cast<uint4*>(orow + c * 32) + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
     }
   }
 

@@ -4,7 +4,8 @@
 //   warp 1      : MMA issuer (one lane issues tcgen05.mma, M=128, N=BN, K=16; accumulators in TMEM)
 //   warp 2      : TMEM allocator (512 columns = 2 accumulator stages x up to 256 columns)
 //   warp 3      : idle
-//   warps 4..11 : epilogue (TMEM -> registers -> fused bias / timestep shift / residuals / GEGLU -> global)
+//   warps 4..19 : epilogue (TMEM -> registers -> fused bias / timestep shift / residuals / GEGLU -> global);
+//                 16 warps because the epilogue is latency bound (dependent TMEM / global loads), not issue bound
 //
 // The 3x3 and temporal convolutions never materialise im2col: the producer shifts the TMA box coordinates per
 // filter tap and lets TMA zero-fill the halo (out-of-bounds) elements.
@@ -19,7 +20,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kNumThreads = 384;
+constexpr int kNumEpiGroups = 4;                        // column groups of epilogue warps (x4 TMEM lane quarters)
+constexpr int kNumThreads = 128 + 128 * kNumEpiGroups;   // 640
 constexpr int kAccCols = 256;  // TMEM columns per accumulator stage
 constexpr int kSmemBudget = 232448;
 
@@ -237,7 +239,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 4 * kNumEpiGroups);  // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -319,7 +321,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2; // which 32-column chunks (even / odd)
+    const int grp = (warp - 4) >> 2;  // which 32-column chunks (ch % kNumEpiGroups == grp)
     const int chunks = g.block_n / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -347,7 +349,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      for (int ch = half; ch < chunks; ch += 2) {
+      for (int ch = grp; ch < chunks; ch += kNumEpiGroups) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kAccCols + ch * 32, v);
         tmem_ld_wait();

@@ -6,52 +6,83 @@
 namespace ttvdm {
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// Thread t owns channel pairs {t, t+T, ...} (T = blockDim.x divides C/2) so its group ids are loop invariant.
+// 16-byte vectorised. A CTA owns `rows_per_cta` consecutive rows of one group instance. Per source tensor (the
+// optional second one is the up-block skip of torch.cat([h, skip], 1)) the first `active = (T / V) * V` threads
+// (V = C_src / 8 vectors per row) keep a FIXED vector column, so group ids / affine coefficients are loop invariant
+// and partial sums live in registers. Partials: fp32 per thread -> smem bins -> one fp64 atomic per (CTA, group).
 
-__device__ __forceinline__ float2 load_pair(const __nv_bfloat16* x1, int c1, int ld1, const __nv_bfloat16* x2,
-                                            int ld2, long long row, int pair) {
-  const int c = pair * 2;
-  const __nv_bfloat16* p = (c < c1) ? (x1 + row * ld1 + c) : (x2 + row * ld2 + (c - c1));
-  return unpack_bf16(*reinterpret_cast<const uint32_t*>(p));
+struct GnSrc {
+  const __nv_bfloat16* x;
+  int c, ld, c_off;  // channels, row stride, channel offset inside the concatenated tensor
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, int ld1,
-                                const __nv_bfloat16* __restrict__ x2, int c2, int ld2, int rows_per_inst,
-                                int rows_per_cta, double* __restrict__ sums) {
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double* __restrict__ sums) {
   __shared__ float bins[64];
-  const int C = c1 + c2;
+  const int C = s1.c + s2.c;
   const int cpg = C / 32;
-  const int pairs = C / 2;
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_inst);
   for (int i = threadIdx.x; i < 64; i += blockDim.x) bins[i] = 0.f;
   __syncthreads();
-  for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
-    float s = 0.f, ss = 0.f;
-    const long long base = (long long)inst * rows_per_inst;
-    for (int r = r0; r < r1; ++r) {
-      const float2 v = load_pair(x1, c1, ld1, x2, ld2, base + r, pair);
-      s += v.x + v.y;
-      ss += v.x * v.x + v.y * v.y;
+  const long long base = (long long)inst * rows_per_inst;
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const GnSrc s = k == 0 ? s1 : s2;
+    if (s.c == 0) continue;
+    const int V = s.c >> 3;
+    const int rpi = blockDim.x / V;  // rows per iteration
+    if ((int)threadIdx.x >= rpi * V) continue;
+    const int col = threadIdx.x % V, rofs = threadIdx.x / V;
+    float sm[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
+    for (int r = r0 + rofs; r < r1; r += rpi) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(s.x + (base + r) * s.ld) + col);
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sm[i] += f[i];
+        sq[i] += f[i] * f[i];
+      }
     }
-    const int grp = (pair * 2) / cpg;  // cpg is even: both channels of a pair share the group
-    atomicAdd(&bins[grp * 2], s);
-    atomicAdd(&bins[grp * 2 + 1], ss);
+    const int c0 = s.c_off + col * 8;
+    // merge the (at most few) groups this vector touches before going to shared memory
+    int g_prev = c0 / cpg;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gi = (c0 + i) / cpg;
+      if (gi != g_prev) {
+        atomicAdd(&bins[g_prev * 2], a);
+        atomicAdd(&bins[g_prev * 2 + 1], b);
+        a = b = 0.f;
+        g_prev = gi;
+      }
+      a += sm[i];
+      b += sq[i];
+    }
+    atomicAdd(&bins[g_prev * 2], a);
+    atomicAdd(&bins[g_prev * 2 + 1], b);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&sums[inst * 64 + i], (double)bins[i]);
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, int ld1,
-                                const __nv_bfloat16* __restrict__ x2, int c2, int ld2, int rows_per_inst,
-                                int rows_per_cta, const double* __restrict__ sums, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu, __nv_bfloat16* __restrict__ out,
-                                int ldo) {
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const double* __restrict__ sums,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                __nv_bfloat16* __restrict__ out, int ldo) {
   __shared__ float s_mean[32], s_rstd[32];
-  const int C = c1 + c2;
+  const int C = s1.c + s2.c;
   const int cpg = C / 32;
-  const int pairs = C / 2;
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_inst);
@@ -65,20 +96,34 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, in
   }
   __syncthreads();
   const long long base = (long long)inst * rows_per_inst;
-  for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
-    const int c = pair * 2;
-    const int grp = c / cpg;
-    const float rs = s_rstd[grp], mu = s_mean[grp];
-    const float a0 = rs * gamma[c], a1 = rs * gamma[c + 1];
-    const float b0 = beta[c] - mu * a0, b1 = beta[c + 1] - mu * a1;
-    for (int r = r0; r < r1; ++r) {
-      const float2 v = load_pair(x1, c1, ld1, x2, ld2, base + r, pair);
-      float y0 = v.x * a0 + b0, y1 = v.y * a1 + b1;
-      if (silu) {
-        y0 = y0 / (1.f + __expf(-y0));
-        y1 = y1 / (1.f + __expf(-y1));
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const GnSrc s = k == 0 ? s1 : s2;
+    if (s.c == 0) continue;
+    const int V = s.c >> 3;
+    const int rpi = blockDim.x / V;
+    if ((int)threadIdx.x >= rpi * V) continue;
+    const int col = threadIdx.x % V, rofs = threadIdx.x / V;
+    const int c0 = s.c_off + col * 8;
+    float ka[8], kb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gi = (c0 + i) / cpg;
+      ka[i] = s_rstd[gi] * gamma[c0 + i];
+      kb[i] = beta[c0 + i] - s_mean[gi] * ka[i];
+    }
+    for (int r = r0 + rofs; r < r1; r += rpi) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(s.x + (base + r) * s.ld) + col);
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(f[i], ka[i], kb[i]);
+        if (silu) y = __fdividef(y, 1.f + __expf(-y));
+        f[i] = y;
       }
-      *reinterpret_cast<uint32_t*>(out + (base + r) * ldo + c) = pack_bf16(y0, y1);
+      *reinterpret_cast<uint4*>(out + (base + r) * ldo + c0) =
+          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     }
   }
 }
@@ -147,13 +192,6 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, i
   }
 }
 
-static int gn_threads(int pairs) {
-  // largest divisor of `pairs` that is a multiple of 32 and <= 512
-  for (int t = 512; t >= 32; t -= 32)
-    if (pairs % t == 0) return t;
-  return 0;
-}
-
 }  // namespace ttvdm
 
 using namespace ttvdm;
@@ -164,27 +202,34 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   if (!p || !p->x1 || !p->out || !p->stats || !p->gamma || !p->beta) return fail(TTVDM_ERR_SHAPE, "groupnorm: null");
   const int c2 = p->x2 ? p->c2 : 0;
   const int C = p->c1 + c2;
-  if (C % 64 != 0 || p->c1 % 2 != 0) return fail(TTVDM_ERR_SHAPE, "groupnorm: C=%d must be a multiple of 64", C);
+  if (C % 32 != 0 || p->c1 % 8 != 0 || c2 % 8 != 0 || p->c1 > 4096 || c2 > 4096)
+    return fail(TTVDM_ERR_SHAPE, "groupnorm: channels %d+%d must be multiples of 8 (sum %% 32 == 0)", p->c1, c2);
+  if (p->ld1 % 8 != 0 || (c2 && p->ld2 % 8 != 0) || p->ldo % 8 != 0)
+    return fail(TTVDM_ERR_SHAPE, "groupnorm: row strides must be multiples of 8 elements");
   if (p->rows <= 0 || p->rows_per_inst <= 0 || p->rows % p->rows_per_inst != 0)
     return fail(TTVDM_ERR_SHAPE, "groupnorm: rows=%d rows_per_inst=%d", p->rows, p->rows_per_inst);
   const int n_inst = p->rows / p->rows_per_inst;
-  const int threads = gn_threads(C / 2);
-  if (threads == 0) return fail(TTVDM_ERR_SHAPE, "groupnorm: unsupported C=%d", C);
-  // fixed chunk => the fp32 partial sums (and therefore the statistics) do not depend on how many sequences this
-  // rank holds: a sharded half-pair reproduces the whole-pair result
-  const int rows_per_cta = 32;
+  // chunk depends on rows_per_inst only (not on how many sequences this rank holds): the fp32 partial sums, and so
+  // the statistics, are identical for a sharded half-pair and the whole pair
+  int rows_per_cta = p->rows_per_inst / 64;
+  if (rows_per_cta < 8) rows_per_cta = 8;
+  if (rows_per_cta > 64) rows_per_cta = 64;
   const int chunks = (p->rows_per_inst + rows_per_cta - 1) / rows_per_cta;
   cudaError_t e = cudaMemsetAsync(p->stats, 0, (size_t)n_inst * 64 * sizeof(double), stream);
   if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "groupnorm: memset: %s", cudaGetErrorString(e));
+  const int vmax = (p->c1 > c2 ? p->c1 : c2) / 8;
+  int threads = 512;
+  if (vmax > threads) return fail(TTVDM_ERR_SHAPE, "groupnorm: more than 4096 channels per source");
+  if (vmax * rows_per_cta < threads) threads = ((vmax * rows_per_cta + 31) / 32) * 32;
+  if (threads < vmax) threads = ((vmax + 31) / 32) * 32;
   dim3 grid(chunks, n_inst);
-  const __nv_bfloat16* x1 = static_cast<const __nv_bfloat16*>(p->x1);
-  const __nv_bfloat16* x2 = static_cast<const __nv_bfloat16*>(p->x2);
-  gn_stats_kernel<<<grid, threads, 0, stream>>>(x1, p->c1, p->ld1, x2, c2, p->ld2, p->rows_per_inst, rows_per_cta,
-                                                static_cast<double*>(p->stats));
+  GnSrc s1{static_cast<const __nv_bfloat16*>(p->x1), p->c1, p->ld1, 0};
+  GnSrc s2{static_cast<const __nv_bfloat16*>(p->x2), c2, p->ld2, p->c1};
+  gn_stats_kernel<<<grid, threads, 0, stream>>>(s1, s2, p->rows_per_inst, rows_per_cta, static_cast<double*>(p->stats));
   TTVDM_CHECK_LAUNCH("gn_stats_kernel");
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(x1, p->c1, p->ld1, x2, c2, p->ld2, p->rows_per_inst, rows_per_cta,
-                                                static_cast<const double*>(p->stats), p->gamma, p->beta, p->eps,
-                                                p->silu, static_cast<__nv_bfloat16*>(p->out), p->ldo);
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(s1, s2, p->rows_per_inst, rows_per_cta,
+                                                static_cast<const double*>(p->stats), p->gamma, p->beta, p->eps, p->silu,
+                                                static_cast<__nv_bfloat16*>(p->out), p->ldo);
   TTVDM_CHECK_LAUNCH("gn_apply_kernel");
   return 0;
 }
