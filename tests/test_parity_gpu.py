@@ -82,7 +82,7 @@ def test_guess_mode_scales_and_timestep_forms(tiny):
         a = unet(sample.cuda(), 0.5, ehs.cuda(), ati.cuda()).sample                      # python float
         b = unet(sample.cuda(), torch.tensor([0.5]).cuda(), ehs.cuda(), ati.cuda()).sample  # 1-dim tensor
     assert rel_l2(d[0], d_ref[0]) < CAP and rel_l2(m, m_ref) < CAP
-    assert torch.equal(a, b)
+    assert rel_l2(a, b) < 1e-5  # identical up to the order of the fp64 GroupNorm atomics
 
 
 def test_zero_init_gesturenet_equals_vl_on_gpu(tiny):

@@ -29,14 +29,25 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   }
   const long long row0 = ((long long)b * F) * S + s;  // frame 0 row; frame f is row0 + f*S
   if (item_ok) {
-    for (int f = 0; f < F; ++f) {
-      const long long row = row0 + (long long)f * S;
-      const uint2 kk = __ldg(reinterpret_cast<const uint2*>(k + row * ldk + head * 64) + l16);
-      const uint2 vv = __ldg(reinterpret_cast<const uint2*>(v + row * ldv + head * 64) + l16);
-      sk[slot][f][l16 * 2] = kk.x;
-      sk[slot][f][l16 * 2 + 1] = kk.y;
-      sv[slot][f][l16 * 2] = vv.x;
-      sv[slot][f][l16 * 2 + 1] = vv.y;
+    // all 2*F row loads are issued before the first shared-memory store (in-order issue would otherwise expose one
+    // full memory latency per frame)
+    uint2 kk[kTaMaxF], vv[kTaMaxF];
+#pragma unroll
+    for (int f = 0; f < kTaMaxF; ++f) {
+      if (f < F) {
+        const long long row = row0 + (long long)f * S;
+        kk[f] = __ldg(reinterpret_cast<const uint2*>(k + row * ldk + head * 64) + l16);
+        vv[f] = __ldg(reinterpret_cast<const uint2*>(v + row * ldv + head * 64) + l16);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kTaMaxF; ++f) {
+      if (f < F) {
+        sk[slot][f][l16 * 2] = kk[f].x;
+        sk[slot][f][l16 * 2 + 1] = kk[f].y;
+        sv[slot][f][l16 * 2] = vv[f].x;
+        sv[slot][f][l16 * 2 + 1] = vv[f].y;
+      }
     }
   }
   __syncthreads();

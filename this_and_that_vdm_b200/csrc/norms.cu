@@ -23,13 +23,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double* __restrict__ sums) {
-  __shared__ float bins[64];
+  __shared__ double bins[64];  // fp64: the order of the atomics then only matters below ~1e-16 relative
   const int C = s1.c + s2.c;
   const int cpg = C / 32;
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_inst);
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) bins[i] = 0.f;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) bins[i] = 0.0;
   __syncthreads();
   const long long base = (long long)inst * rows_per_inst;
 #pragma unroll 1
@@ -43,14 +43,21 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double*
     float sm[8], sq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
-    for (int r = r0 + rofs; r < r1; r += rpi) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(s.x + (base + r) * s.ld) + col);
-      float f[8];
-      unpack8(u, f);
+    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
+      uint4 u[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sm[i] += f[i];
-        sq[i] += f[i] * f[i];
+      for (int b = 0; b < 4; ++b)  // 4 independent 16-byte loads in flight per thread
+        u[b] = (r + b * rpi < r1) ? __ldg(reinterpret_cast<const uint4*>(s.x + (base + r + b * rpi) * s.ld) + col)
+                                  : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float f[8];
+        unpack8(u[b], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sm[i] += f[i];
+          sq[i] += f[i] * f[i];
+        }
       }
     }
     const int c0 = s.c_off + col * 8;
@@ -61,19 +68,19 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double*
     for (int i = 0; i < 8; ++i) {
       const int gi = (c0 + i) / cpg;
       if (gi != g_prev) {
-        atomicAdd(&bins[g_prev * 2], a);
-        atomicAdd(&bins[g_prev * 2 + 1], b);
+        atomicAdd(&bins[g_prev * 2], (double)a);
+        atomicAdd(&bins[g_prev * 2 + 1], (double)b);
         a = b = 0.f;
         g_prev = gi;
       }
       a += sm[i];
       b += sq[i];
     }
-    atomicAdd(&bins[g_prev * 2], a);
-    atomicAdd(&bins[g_prev * 2 + 1], b);
+    atomicAdd(&bins[g_prev * 2], (double)a);
+    atomicAdd(&bins[g_prev * 2 + 1], (double)b);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&sums[inst * 64 + i], (double)bins[i]);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&sums[inst * 64 + i], bins[i]);
 }
 
 __global__ void __launch_bounds__(512)
@@ -112,18 +119,26 @@ gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const d
       ka[i] = s_rstd[gi] * gamma[c0 + i];
       kb[i] = beta[c0 + i] - s_mean[gi] * ka[i];
     }
-    for (int r = r0 + rofs; r < r1; r += rpi) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(s.x + (base + r) * s.ld) + col);
-      float f[8];
-      unpack8(u, f);
+    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
+      uint4 u[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y = fmaf(f[i], ka[i], kb[i]);
-        if (silu) y = __fdividef(y, 1.f + __expf(-y));
-        f[i] = y;
+      for (int b = 0; b < 4; ++b)
+        u[b] = (r + b * rpi < r1) ? __ldg(reinterpret_cast<const uint4*>(s.x + (base + r + b * rpi) * s.ld) + col)
+                                  : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (r + b * rpi >= r1) break;
+        float f[8];
+        unpack8(u[b], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = fmaf(f[i], ka[i], kb[i]);
+          if (silu) y = __fdividef(y, 1.f + __expf(-y));
+          f[i] = y;
+        }
+        *reinterpret_cast<uint4*>(out + (base + r + b * rpi) * ldo + c0) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
       }
-      *reinterpret_cast<uint4*>(out + (base + r) * ldo + c0) =
-          make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
     }
   }
 }
