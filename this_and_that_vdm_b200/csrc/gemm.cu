@@ -9,6 +9,7 @@
 //
 // The 3x3 and temporal convolutions never materialise im2col: the producer shifts the TMA box coordinates per
 // filter tap and lets TMA zero-fill the halo (out-of-bounds) elements.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -24,6 +25,8 @@ constexpr int kNumEpiGroups = 4;                        // column groups of epil
 constexpr int kNumThreads = 128 + 128 * kNumEpiGroups;   // 640
 constexpr int kAccCols = 256;  // TMEM columns per accumulator stage
 constexpr int kSmemBudget = 232448;
+constexpr int kEpiWarps = 4 * kNumEpiGroups;
+constexpr int kEpiBufBytes = 32 * 128;  // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled (one TMA box)
 
 struct GemmArgs {
   int mode;
@@ -46,6 +49,8 @@ struct GemmArgs {
   int geglu;
   void* out;
   int ldo, out_fp32, act;
+  int tma_epi;        // 1: residual tile in / output tile out through per-warp smem + TMA (coalesced, asynchronous)
+  int epi_box_w;      // CONV: pixels per image row covered by a warp's 32 tile rows (min(TW, 32))
 };
 
 struct TileCoord {
@@ -223,7 +228,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-            const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+            const __grid_constant__ CUtensorMap tmRes, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -233,6 +239,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 3;  // [kEpiWarps] residual tile landed in the warp's staging buffer
   uint8_t* tiles = smem + 1024;
   const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
 
@@ -245,12 +252,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (g.tma_epi) {
+      tma_prefetch_desc(&tmOut);
+      tma_prefetch_desc(&tmRes);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4 * kNumEpiGroups);  // one arrival per epilogue warp
@@ -337,6 +349,162 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = (warp - 4) >> 2;  // which 32-column chunks (ch % kNumEpiGroups == grp)
     const int chunks = g.block_n / 32;
+    if (g.tma_epi) {
+      // ---- TMA epilogue: each warp owns a 32-row x 64-column strip per tile. The residual strip is fetched by TMA
+      // into the warp's 128B-swizzled staging buffer while the tile's MMAs run, the fp32 epilogue math happens in
+      // registers (one row per lane), and the bf16 strip leaves through a TMA store — every global access is a full
+      // 128-byte line and none of them occupies the LSU.
+      const int ew = warp - 4;
+      uint8_t* sbuf = tiles + g.stages * stage_bytes + ew * kEpiBufBytes;
+      uint64_t* rbar = &res_bar[ew];
+      const bool has_res = g.res1 != nullptr;
+      const int strip = grp * 64;  // first accumulator column of this warp's strip inside the tile
+      uint32_t rphase = 0;         // parity of rbar: flips only on tiles where this warp actually fetched a residual
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const TileCoord t = tile_coord(g, tile);
+        const int col0 = t.n0 + strip;
+        const bool active = (strip < g.block_n) && (col0 < g.N);
+        // box coordinates of the warp's 32 tile rows
+        int c1, c2 = 0, c3 = 0;
+        if (g.mode == TTVDM_A_LINEAR) {
+          c1 = t.m0 + q * 32;
+        } else if (g.mode == TTVDM_A_CONV3X3) {
+          const int r0 = q * 32;
+          c1 = t.w0 + (r0 % g.TW);  // TW >= 32: column offset inside the pixel-box row; TW < 32: 0
+          c2 = t.h0 + r0 / g.TW;
+          c3 = t.img;
+        } else {
+          c1 = t.w0 + q * 32;
+          c2 = t.h0;
+          c3 = t.img;
+        }
+        long long my_row;
+        bool my_valid;
+        {
+          const int r = q * 32 + lane;
+          if (g.mode == TTVDM_A_LINEAR) {
+            my_row = t.m0 + r;
+            my_valid = my_row < g.M;
+          } else if (g.mode == TTVDM_A_CONV3X3) {
+            const int th = r / g.TW, tw = r - th * g.TW;
+            my_valid = (t.h0 + th < g.H) && (t.w0 + tw < g.W);
+            my_row = ((long long)t.img * g.H + t.h0 + th) * g.W + t.w0 + tw;
+          } else {
+            my_valid = (t.w0 + r) < g.W;
+            my_row = ((long long)t.img * g.H + t.h0) * g.W + t.w0 + r;
+          }
+        }
+        if (active) {
+          if (lane == 0) {
+            tma_store_wait_read();  // the previous tile's store has finished reading the staging buffer
+            if (has_res) {
+              mbar_expect_tx(rbar, kEpiBufBytes);
+              if (g.mode == TTVDM_A_LINEAR) tma_load_2d(sbuf, &tmRes, rbar, col0, c1);
+              else tma_load_4d(sbuf, &tmRes, rbar, col0, c1, c2, c3);
+            }
+          }
+          __syncwarp();
+        }
+        const float* rv = nullptr;
+        if (g.rowvec != nullptr && my_valid) rv = g.rowvec + (my_row / g.rows_per_vec) * g.ldrv;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (active) {
+          if (has_res) {
+            mbar_wait(rbar, rphase);
+            rphase ^= 1;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int ch_col = strip + cc * 32;
+            if (ch_col >= g.block_n) break;  // warp-uniform (BN = 160 / 96 / 32: last strip is one chunk wide)
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kAccCols + ch_col, v);
+            tmem_ld_wait();
+            const int gc = t.n0 + ch_col;  // global column of v[0]
+            float a[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+            if (gc + 32 <= g.N) {
+              if (g.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc + i));
+                  a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+                }
+              }
+              if (rv != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + gc + i));
+                  a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (gc + i < g.N) a[i] += (g.bias ? g.bias[gc + i] : 0.f) + (rv ? rv[gc + i] : 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] *= g.s0;
+            if (g.res2 != nullptr && my_valid && gc + 32 <= g.N) {
+              const __nv_bfloat16* rp = g.res2 + my_row * g.ldr2 + gc;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16(w4[j]);
+                  a[i * 8 + j * 2] += g.s2 * f.x;
+                  a[i * 8 + j * 2 + 1] += g.s2 * f.y;
+                }
+              }
+            }
+            // staging row = lane; 16-byte pieces cc*4 .. cc*4+3, XOR-swizzled with (row & 7) (TMA SWIZZLE_128B)
+            uint8_t* srow = sbuf + lane * 128;
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+              uint4* sp = reinterpret_cast<uint4*>(srow + (((cc * 4 + pc) ^ (lane & 7)) << 4));
+              float o[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o[k] = a[pc * 8 + k];
+              if (has_res) {
+                const uint4 u = *sp;
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_bf16(w4[k]);
+                  o[2 * k] += g.s1 * f.x;
+                  o[2 * k + 1] += g.s1 * f.y;
+                }
+              }
+              if (g.act == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
+              }
+              *sp = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulator stage is free for the next tile's MMAs
+        if (active) {
+          fence_async_smem();  // every lane: its staging writes become visible to the async proxy
+          __syncwarp();
+          if (lane == 0) {
+            if (g.mode == TTVDM_A_LINEAR) tma_store_2d(&tmOut, sbuf, col0, c1);
+            else tma_store_4d(&tmOut, sbuf, col0, c1, c2, c3);
+            tma_store_commit();
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait_read();
+    } else {
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -375,6 +543,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+      }
   }
 
   tc_fence_before();
@@ -421,9 +590,42 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   g.kc_per_tap = (p->k1 + k2) / kBlockK;
   g.taps = p->mode == TTVDM_A_CONV3X3 ? 9 : (p->mode == TTVDM_A_TCONV3 ? 3 : 1);
   g.block_n = pick_block_n(p->N);
+  const int ktot_pre = g.taps * (p->k1 + k2);
+  int want_tma = 0;
+  // long-K GEMMs are MMA bound: they keep the deeper operand pipeline (no staging buffers) and the direct epilogue
+  if (g.block_n % 64 == 0 && p->N >= 64 && ktot_pre <= 2048) {
+    want_tma = 1;
+  } else if (ktot_pre <= 640 && p->N >= 64) {
+    // short-K GEMMs are epilogue / memory bound: take a 64-column-granular tile (fewest N tiles, then least padding)
+    // so the TMA epilogue applies, even if that pads the last N tile
+    int best = 0, best_tiles = 1 << 30;
+    double best_eff = -1.0;
+    const int cands[] = {256, 192, 128, 64};
+    for (int c : cands) {
+      const int nt = (p->N + c - 1) / c;
+      const double eff = (double)p->N / ((double)nt * c);
+      if (nt < best_tiles || (nt == best_tiles && eff > best_eff + 1e-9)) {
+        best = c;
+        best_tiles = nt;
+        best_eff = eff;
+      }
+    }
+    g.block_n = best;
+    want_tma = 1;
+  }
   g.n_tiles = (p->N + g.block_n - 1) / g.block_n;
   const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
-  g.stages = (kSmemBudget - 2048) / stage_bytes;
+  // TMA epilogue: bf16 output, no GEGLU, 16-byte aligned rows and bases (TMA global-memory constraints)
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  g.tma_epi = (want_tma && !p->out_fp32 && !p->geglu && p->N % 8 == 0 && p->ldo % 8 == 0 && al16(p->out) &&
+               (!p->res1 || (p->ldr1 % 8 == 0 && al16(p->res1))) && (!p->res2 || (p->res1 && p->ldr2 % 8 == 0 && al16(p->res2))))
+                  ? 1 : 0;
+  {
+    static const int force_direct = getenv("TTVDM_DIRECT_EPILOGUE") != nullptr;  // A/B switch for profiling only
+    if (force_direct) g.tma_epi = 0;
+  }
+  const int epi_bytes = g.tma_epi ? kEpiWarps * kEpiBufBytes : 0;
+  g.stages = (kSmemBudget - 2048 - epi_bytes) / stage_bytes;
   if (g.stages > kMaxStages) g.stages = kMaxStages;
   const int ktot = g.taps * (p->k1 + k2);
 
@@ -488,6 +690,29 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     uint32_t box[2] = {kBlockK, (uint32_t)g.block_n};
     if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box))) return rc;
   }
+  CUtensorMap tmOut = tmB, tmRes = tmB;
+  if (g.tma_epi) {
+    // one box = the 32 tile rows of an epilogue warp x 64 columns
+    auto make_io = [&](CUtensorMap* m, const void* base, int ld) -> int {
+      if (p->mode == TTVDM_A_LINEAR) {
+        uint64_t dims[2] = {(uint64_t)p->N, (uint64_t)p->M};
+        uint64_t str[1] = {(uint64_t)ld * 2};
+        uint32_t box[2] = {64, 32};
+        return make_tmap_bf16(m, base, 2, dims, str, box);
+      }
+      uint64_t dims[4] = {(uint64_t)p->N, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->n_img};
+      uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * p->W, (uint64_t)ld * 2 * p->W * p->H};
+      uint32_t bw = 32, bh = 1;
+      if (p->mode == TTVDM_A_CONV3X3 && g.TW < 32) {
+        bw = (uint32_t)g.TW;
+        bh = 32u / (uint32_t)g.TW;
+      }
+      uint32_t box[4] = {64, bw, bh, 1};
+      return make_tmap_bf16(m, base, 4, dims, str, box);
+    };
+    if ((rc = make_io(&tmOut, p->out, p->ldo))) return rc;
+    if (p->res1 && (rc = make_io(&tmRes, p->res1, p->ldr1))) return rc;
+  }
   g.bias = p->bias;
   g.rowvec = p->rowvec;
   g.rows_per_vec = p->rows_per_vec > 0 ? p->rows_per_vec : 1;
@@ -508,7 +733,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (!p->out_fp32 && ((p->ldo % 8) != 0 && p->N >= 32)) return fail(TTVDM_ERR_SHAPE, "gemm: ldo %% 8 != 0");
   if ((p->res1 && p->ldr1 % 8) || (p->res2 && p->ldr2 % 8)) return fail(TTVDM_ERR_SHAPE, "gemm: ldr %% 8 != 0");
 
-  const size_t smem = 2048 + (size_t)g.stages * stage_bytes;
+  const size_t smem = 2048 + (size_t)g.stages * stage_bytes + epi_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -517,7 +742,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   }
   const int num_tiles = g.m_tiles * g.n_tiles;
   const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, g);
+  gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
   TTVDM_CHECK_LAUNCH("gemm_kernel");
   return 0;
 }

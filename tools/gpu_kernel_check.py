@@ -240,6 +240,8 @@ CASES = [
     ("gemm_linear_geglu", lambda: case_gemm_linear(M=515, N=2560, K=320, geglu=True)),
     ("gemm_linear_concatK", lambda: case_gemm_linear(M=300, N=640, K=1280, a2=True)),
     ("gemm_linear_raggedN", lambda: case_gemm_linear(M=130, N=200, K=64)),
+    ("gemm_linear_res_partialN", lambda: case_gemm_linear(M=128 * 300 + 17, N=320, K=320, res=True)),
+    ("gemm_linear_res_640", lambda: case_gemm_linear(M=128 * 150, N=640, K=640, res=True)),
     ("gemm_linear_multitile", lambda: case_gemm_linear(M=128 * 200, N=1920, K=640, bias=False)),
     ("conv3x3_small", lambda: case_conv3x3()),
     ("conv3x3_L0", lambda: case_conv3x3(n=2, H=32, W=48, Cin=320, Cout=320)),
