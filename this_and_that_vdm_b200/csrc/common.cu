@@ -49,7 +49,7 @@ int ensure_init() {
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, bool swizzle128) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5];
@@ -65,7 +65,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
     if (gstr[i] % 16 != 0) return fail(TTVDM_ERR_SHAPE, "tensor map stride %d (%llu B) not a multiple of 16", i,
                                        (unsigned long long)gstr[i]);
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(TTVDM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

@@ -33,7 +33,7 @@ int ensure_init();
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, bool swizzle128 = true);
 
 #define TTVDM_CHECK_LAUNCH(name)                                                                  \
   do {                                                                                            \

@@ -49,6 +49,8 @@ struct GemmArgs {
   int geglu;
   void* out;
   int ldo, out_fp32, act;
+  int b_resident;     // 1: this CTA keeps ONE N tile of W (all K chunks) in smem and only streams A tiles
+  int ctas_per_n;     // b_resident: CTAs sharing an N tile
   int tma_epi;        // 1: residual tile in / output tile out through per-warp smem + TMA (coalesced, asynchronous)
   int epi_box_w;      // CONV: pixels per image row covered by a warp's 32 tile rows (min(TW, 32))
 };
@@ -87,6 +89,17 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
 
 // exact-erf GELU (diffusers GEGLU uses F.gelu, erf form) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7,
 // two MUFU ops + 8 FMAs instead of libdevice erff's ~30 instructions; the GEGLU epilogue is instruction bound)
+// Persistent tile schedule. Default: tile = blockIdx.x + i * gridDim.x over (m, n) with n fastest. B-resident: the CTA is
+// pinned to N tile (blockIdx.x % n_tiles) and walks M tiles blockIdx.x / n_tiles + i * ctas_per_n.
+__device__ __forceinline__ int sched_tile(const GemmArgs& g, int i) {
+  if (!g.b_resident) {
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    return tile < g.m_tiles * g.n_tiles ? tile : -1;
+  }
+  const int mt = (int)blockIdx.x / g.n_tiles + i * g.ctas_per_n;
+  return mt < g.m_tiles ? mt * g.n_tiles + ((int)blockIdx.x % g.n_tiles) : -1;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
@@ -240,12 +253,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* res_bar = tempty_bar + 3;  // [kEpiWarps] residual tile landed in the warp's staging buffer
+  uint64_t* bres_bar = res_bar + kEpiWarps;  // resident W tile landed
   uint8_t* tiles = smem + 1024;
-  const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
+  const int b_chunk_bytes = g.block_n * kBlockK * 2;
+  const int stage_bytes = g.b_resident ? kABytes : kABytes + b_chunk_bytes;
+  uint8_t* bres = tiles + g.stages * stage_bytes;  // b_resident only (never together with the TMA epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = g.m_tiles * g.n_tiles;
   const int num_kc = g.taps * g.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
@@ -263,6 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(bres_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4 * kNumEpiGroups);  // one arrival per epilogue warp
@@ -279,14 +295,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (g.b_resident && lane == 0) {
+      // the CTA's N tile of W: all K chunks, once
+      const int n0 = (blockIdx.x % g.n_tiles) * g.block_n;
+      mbar_expect_tx(bres_bar, num_kc * b_chunk_bytes);
+      for (int kc = 0; kc < num_kc; ++kc) tma_load_2d(bres + kc * b_chunk_bytes, &tmB, bres_bar, kc * kBlockK, n0);
+    }
+    for (int ti = 0;; ++ti) {
+      const int tile = sched_tile(g, ti);
+      if (tile < 0) break;
       const TileCoord t = tile_coord(g, tile);
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = tiles + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
           const int tap = kc / g.kc_per_tap;
           const int cc = kc - tap * g.kc_per_tap;
           if (g.mode == TTVDM_A_LINEAR) {
@@ -300,7 +324,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
           }
-          tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
+          if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
         }
         __syncwarp();
         if (++stage == g.stages) {
@@ -315,7 +339,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    if (g.b_resident) mbar_wait(bres_bar, 0);
+    for (;; ++it) {
+      const int tile = sched_tile(g, it);
+      if (tile < 0) break;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -326,7 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = g.b_resident ? smem_u32(bres + kc * b_chunk_bytes) : sa + kABytes;
           const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
           const uint64_t b_desc = make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
@@ -361,7 +388,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int strip = grp * 64;  // first accumulator column of this warp's strip inside the tile
       uint32_t rphase = 0;         // parity of rbar: flips only on tiles where this warp actually fetched a residual
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (;; ++it) {
+        const int tile = sched_tile(g, it);
+        if (tile < 0) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const TileCoord t = tile_coord(g, tile);
@@ -448,6 +477,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int i = 0; i < 32; ++i)
                 if (gc + i < g.N) a[i] += (g.bias ? g.bias[gc + i] : 0.f) + (rv ? rv[gc + i] : 0.f);
             }
+            if (g.geglu) {
+              // interleaved (hidden, gate) columns -> 16 outputs = 32 bytes of the 64-byte staging row (no swizzle)
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float o0 = a[4 * j] * gelu_erf(a[4 * j + 1]);
+                const float o1 = a[4 * j + 2] * gelu_erf(a[4 * j + 3]);
+                pk[j] = pack_bf16(g.s0 * o0, g.s0 * o1);
+              }
+              uint4* sp = reinterpret_cast<uint4*>(sbuf + lane * 64 + cc * 32);
+              sp[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              sp[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              continue;
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] *= g.s0;
             if (g.res2 != nullptr && my_valid && gc + 32 <= g.N) {
@@ -497,7 +540,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_async_smem();  // every lane: its staging writes become visible to the async proxy
           __syncwarp();
           if (lane == 0) {
-            if (g.mode == TTVDM_A_LINEAR) tma_store_2d(&tmOut, sbuf, col0, c1);
+            if (g.mode == TTVDM_A_LINEAR) tma_store_2d(&tmOut, sbuf, g.geglu ? (col0 >> 1) : col0, c1);
             else tma_store_4d(&tmOut, sbuf, col0, c1, c2, c3);
             tma_store_commit();
           }
@@ -506,7 +549,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) tma_store_wait_read();
     } else {
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      const int tile = sched_tile(g, it);
+      if (tile < 0) break;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const TileCoord t = tile_coord(g, tile);
@@ -593,7 +638,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   const int ktot_pre = g.taps * (p->k1 + k2);
   int want_tma = 0;
   // long-K GEMMs are MMA bound: they keep the deeper operand pipeline (no staging buffers) and the direct epilogue
-  if (g.block_n % 64 == 0 && p->N >= 64 && ktot_pre <= 2048) {
+  if (g.block_n % 64 == 0 && p->N >= 64 && (ktot_pre <= 2048 || p->geglu)) {
     want_tma = 1;
   } else if (ktot_pre <= 640 && p->N >= 64) {
     // short-K GEMMs are epilogue / memory bound: take a 64-column-granular tile (fewest N tiles, then least padding)
@@ -617,7 +662,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   const int stage_bytes = kABytes + g.block_n * kBlockK * 2;
   // TMA epilogue: bf16 output, no GEGLU, 16-byte aligned rows and bases (TMA global-memory constraints)
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  g.tma_epi = (want_tma && !p->out_fp32 && !p->geglu && p->N % 8 == 0 && p->ldo % 8 == 0 && al16(p->out) &&
+  g.tma_epi = (want_tma && !p->out_fp32 && (!p->geglu || (p->mode == TTVDM_A_LINEAR && p->N % 16 == 0)) && p->N % 8 == 0 && p->ldo % 8 == 0 && al16(p->out) &&
                (!p->res1 || (p->ldr1 % 8 == 0 && al16(p->res1))) && (!p->res2 || (p->res1 && p->ldr2 % 8 == 0 && al16(p->res2))))
                   ? 1 : 0;
   {
@@ -625,7 +670,24 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     if (force_direct) g.tma_epi = 0;
   }
   const int epi_bytes = g.tma_epi ? kEpiWarps * kEpiBufBytes : 0;
-  g.stages = (kSmemBudget - 2048 - epi_bytes) / stage_bytes;
+  // B-resident schedule for short-K, many-M-tile GEMMs with the direct epilogue (GEGLU): re-streaming the W tile from
+  // L2 for every 128 rows makes them L2->SM bandwidth bound; pinning one N tile per CTA cuts the traffic per tile from
+  // (128 + BN) * K to 128 * K elements
+  const int b_res_bytes = g.taps * ((p->k1 + k2) / kBlockK) * g.block_n * kBlockK * 2;
+  int stage_b = stage_bytes;
+  g.b_resident = 0;
+  if (!g.tma_epi && p->mode == TTVDM_A_LINEAR && b_res_bytes <= 160 * 1024 && g.n_tiles <= g_num_sms / 4 &&
+      (p->M + kBlockM - 1) / kBlockM >= 8 * (g_num_sms / g.n_tiles)) {
+    g.b_resident = 1;
+    g.ctas_per_n = g_num_sms / g.n_tiles;
+    stage_b = kABytes;
+  }
+  g.stages = (kSmemBudget - 2048 - epi_bytes - (g.b_resident ? b_res_bytes : 0)) / stage_b;
+  if (g.stages < 2) {
+    g.b_resident = 0;
+    stage_b = stage_bytes;
+    g.stages = (kSmemBudget - 2048 - epi_bytes) / stage_b;
+  }
   if (g.stages > kMaxStages) g.stages = kMaxStages;
   const int ktot = g.taps * (p->k1 + k2);
 
@@ -710,7 +772,15 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
       uint32_t box[4] = {64, bw, bh, 1};
       return make_tmap_bf16(m, base, 4, dims, str, box);
     };
-    if ((rc = make_io(&tmOut, p->out, p->ldo))) return rc;
+    if (p->geglu) {
+      // GEGLU halves the columns: a warp's 64 accumulator columns become a 32-column (64-byte) box, no swizzle
+      uint64_t dims[2] = {(uint64_t)(p->N / 2), (uint64_t)p->M};
+      uint64_t str[1] = {(uint64_t)p->ldo * 2};
+      uint32_t box[2] = {32, 32};
+      if ((rc = make_tmap_bf16(&tmOut, p->out, 2, dims, str, box, false))) return rc;
+    } else if ((rc = make_io(&tmOut, p->out, p->ldo))) {
+      return rc;
+    }
     if (p->res1 && (rc = make_io(&tmRes, p->res1, p->ldr1))) return rc;
   }
   g.bias = p->bias;
@@ -733,7 +803,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (!p->out_fp32 && ((p->ldo % 8) != 0 && p->N >= 32)) return fail(TTVDM_ERR_SHAPE, "gemm: ldo %% 8 != 0");
   if ((p->res1 && p->ldr1 % 8) || (p->res2 && p->ldr2 % 8)) return fail(TTVDM_ERR_SHAPE, "gemm: ldr %% 8 != 0");
 
-  const size_t smem = 2048 + (size_t)g.stages * stage_bytes + epi_bytes;
+  const size_t smem = 2048 + (size_t)g.stages * stage_b + epi_bytes + (g.b_resident ? b_res_bytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -741,7 +811,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     attr_set = true;
   }
   const int num_tiles = g.m_tiles * g.n_tiles;
-  const int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  const int grid = g.b_resident ? g.ctas_per_n * g.n_tiles : (num_tiles < g_num_sms ? num_tiles : g_num_sms);
   gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
   TTVDM_CHECK_LAUNCH("gemm_kernel");
   return 0;

@@ -238,6 +238,7 @@ CASES = [
     ("gemm_linear_320", lambda: case_gemm_linear()),
     ("gemm_linear_bigN_res", lambda: case_gemm_linear(M=777, N=1280, K=640, res=True)),
     ("gemm_linear_geglu", lambda: case_gemm_linear(M=515, N=2560, K=320, geglu=True)),
+    ("gemm_linear_geglu_bresident", lambda: case_gemm_linear(M=128 * 117 + 5, N=2560, K=320, geglu=True)),
     ("gemm_linear_concatK", lambda: case_gemm_linear(M=300, N=640, K=1280, a2=True)),
     ("gemm_linear_raggedN", lambda: case_gemm_linear(M=130, N=200, K=64)),
     ("gemm_linear_res_partialN", lambda: case_gemm_linear(M=128 * 300 + 17, N=320, K=320, res=True)),
