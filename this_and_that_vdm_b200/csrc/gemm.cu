@@ -49,6 +49,7 @@ struct GemmArgs {
   int geglu;
   void* out;
   int ldo, out_fp32, act;
+  int n_img;          // images (CONV) / batch (TCONV): tiles beyond it are padding of an odd CTA pair
   int b_resident;     // 1: this CTA keeps ONE N tile of W (all K chunks) in smem and only streams A tiles
   int ctas_per_n;     // b_resident: CTAs sharing an N tile
   int tma_epi;        // 1: residual tile in / output tile out through per-warp smem + TMA (coalesced, asynchronous)
@@ -91,7 +92,16 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile) {
 // two MUFU ops + 8 FMAs instead of libdevice erff's ~30 instructions; the GEGLU epilogue is instruction bound)
 // Persistent tile schedule. Default: tile = blockIdx.x + i * gridDim.x over (m, n) with n fastest. B-resident: the CTA is
 // pinned to N tile (blockIdx.x % n_tiles) and walks M tiles blockIdx.x / n_tiles + i * ctas_per_n.
-__device__ __forceinline__ int sched_tile(const GemmArgs& g, int i) {
+template <int kCtas>
+__device__ __forceinline__ int sched_tile(const GemmArgs& g, int i, int cta_rank) {
+  if (kCtas == 2) {
+    // CTA pair: both CTAs walk the same pair-tiles; CTA r owns M tile 2*pm + r (may be one past the end: all-padding tile)
+    const int pt = ((int)blockIdx.x >> 1) + i * ((int)gridDim.x >> 1);
+    const int pm_tiles = (g.m_tiles + 1) >> 1;
+    if (pt >= pm_tiles * g.n_tiles) return -1;
+    const int pm = pt / g.n_tiles;
+    return (2 * pm + cta_rank) * g.n_tiles + (pt - pm * g.n_tiles);
+  }
   if (!g.b_resident) {
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     return tile < g.m_tiles * g.n_tiles ? tile : -1;
@@ -239,6 +249,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
     }
   }
 
+template <int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -255,8 +266,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* res_bar = tempty_bar + 3;  // [kEpiWarps] residual tile landed in the warp's staging buffer
   uint64_t* bres_bar = res_bar + kEpiWarps;  // resident W tile landed
   uint8_t* tiles = smem + 1024;
-  const int b_chunk_bytes = g.block_n * kBlockK * 2;
+  const int b_chunk_bytes = (g.block_n / kCtas) * kBlockK * 2;  // CTA pair: each CTA stages half of the W tile
   const int stage_bytes = g.b_resident ? kABytes : kABytes + b_chunk_bytes;
+  const int cta_rank = kCtas == 2 ? (int)cluster_ctarank() : 0;
   uint8_t* bres = tiles + g.stages * stage_bytes;  // b_resident only (never together with the TMA epilogue)
 
   const int warp = threadIdx.x >> 5;
@@ -281,13 +293,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     mbar_init(bres_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4 * kNumEpiGroups);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 4 * kNumEpiGroups * kCtas);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if (kCtas == 2) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kCtas == 2) cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -302,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kc = 0; kc < num_kc; ++kc) tma_load_2d(bres + kc * b_chunk_bytes, &tmB, bres_bar, kc * kBlockK, n0);
     }
     for (int ti = 0;; ++ti) {
-      const int tile = sched_tile(g, ti);
+      const int tile = sched_tile<kCtas>(g, ti, cta_rank);
       if (tile < 0) break;
       const TileCoord t = tile_coord(g, tile);
       for (int kc = 0; kc < num_kc; ++kc) {
@@ -310,21 +326,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
           uint8_t* sa = tiles + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
+          if (kCtas == 1) mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
+          else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
           const int tap = kc / g.kc_per_tap;
           const int cc = kc - tap * g.kc_per_tap;
           if (g.mode == TTVDM_A_LINEAR) {
-            if (cc < g.kc_a1)
-              tma_load_2d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.m0);
-            else
-              tma_load_2d(sa, &tmA2, &full_bar[stage], (cc - g.kc_a1) * kBlockK, t.m0);
+            const CUtensorMap* ma = (cc < g.kc_a1) ? &tmA : &tmA2;
+            const int ck = (cc < g.kc_a1 ? cc : cc - g.kc_a1) * kBlockK;
+            if (kCtas == 1) tma_load_2d(sa, ma, &full_bar[stage], ck, t.m0);
+            else tma_load_2d_pair(sa, ma, &full_bar[stage], ck, t.m0);
           } else if (g.mode == TTVDM_A_CONV3X3) {
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
+            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
+            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
           } else {
-            tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
+            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
+            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
           }
-          if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
+          if (kCtas == 2) tma_load_2d_pair(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0 + cta_rank * (g.block_n >> 1));
+          else if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
         }
         __syncwarp();
         if (++stage == g.stages) {
@@ -333,15 +353,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(kBlockM, g.block_n);
+  } else if (warp == 1 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    const uint32_t idesc = make_idesc_bf16(kBlockM * kCtas, g.block_n);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     if (g.b_resident) mbar_wait(bres_bar, 0);
     for (;; ++it) {
-      const int tile = sched_tile(g, it);
+      const int tile = sched_tile<kCtas>(g, it, cta_rank);
       if (tile < 0) break;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -359,10 +379,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+            if (kCtas == 1) tc_mma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
+            else tc_mma_ss_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);
-          if (kc == num_kc - 1) tc_commit(&tfull_bar[acc]);
+          if (kCtas == 1) {
+            tc_commit(&empty_bar[stage]);
+            if (kc == num_kc - 1) tc_commit(&tfull_bar[acc]);
+          } else {  // multicast: frees the stage / publishes the accumulator in BOTH CTAs
+            tc_commit_pair(&empty_bar[stage]);
+            if (kc == num_kc - 1) tc_commit_pair(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
         if (++stage == g.stages) {
@@ -389,7 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t rphase = 0;         // parity of rbar: flips only on tiles where this warp actually fetched a residual
       int it = 0;
       for (;; ++it) {
-        const int tile = sched_tile(g, it);
+        const int tile = sched_tile<kCtas>(g, it, cta_rank);
         if (tile < 0) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -419,10 +445,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             my_valid = my_row < g.M;
           } else if (g.mode == TTVDM_A_CONV3X3) {
             const int th = r / g.TW, tw = r - th * g.TW;
-            my_valid = (t.h0 + th < g.H) && (t.w0 + tw < g.W);
+            my_valid = (t.h0 + th < g.H) && (t.w0 + tw < g.W) && (t.img < g.n_img);
             my_row = ((long long)t.img * g.H + t.h0 + th) * g.W + t.w0 + tw;
           } else {
-            my_valid = (t.w0 + r) < g.W;
+            my_valid = ((t.w0 + r) < g.W) && (t.img < g.n_img);
             my_row = ((long long)t.img * g.H + t.h0) * g.W + t.w0 + r;
           }
         }
@@ -535,7 +561,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);  // accumulator stage is free for the next tile's MMAs
+        if (lane == 0) {  // accumulator stage is free for the next tile's MMAs (the leader's MMA warp counts both CTAs)
+          if (kCtas == 1) mbar_arrive(&tempty_bar[acc]);
+          else mbar_arrive_cluster(&tempty_bar[acc], 0);
+        }
         if (active) {
           fence_async_smem();  // every lane: its staging writes become visible to the async proxy
           __syncwarp();
@@ -550,7 +579,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
     int it = 0;
     for (;; ++it) {
-      const int tile = sched_tile(g, it);
+      const int tile = sched_tile<kCtas>(g, it, cta_rank);
       if (tile < 0) break;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -564,11 +593,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if (g.mode == TTVDM_A_CONV3X3) {
         const int th = r / g.TW, tw = r - th * g.TW;
         const int h = t.h0 + th, w = t.w0 + tw;
-        valid = (h < g.H) && (w < g.W);
+        valid = (h < g.H) && (w < g.W) && (t.img < g.n_img);
         out_row = ((long long)t.img * g.H + h) * g.W + w;
       } else {
         const int s = t.w0 + r;
-        valid = s < g.W;
+        valid = (s < g.W) && (t.img < g.n_img);
         out_row = ((long long)t.img * g.H + t.h0) * g.W + s;
       }
       const float* rv = nullptr;
@@ -586,14 +615,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCtas == 1) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(&tempty_bar[acc], 0);
+      }
     }
       }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (kCtas == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other can still signal it
+  if (warp == 2) {
+    if (kCtas == 2) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 static int pick_block_n(int N) {
@@ -783,6 +819,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     }
     if (p->res1 && (rc = make_io(&tmRes, p->res1, p->ldr1))) return rc;
   }
+  g.n_img = p->mode == TTVDM_A_LINEAR ? 1 : p->n_img;
   g.bias = p->bias;
   g.rowvec = p->rowvec;
   g.rows_per_vec = p->rows_per_vec > 0 ? p->rows_per_vec : 1;
@@ -803,16 +840,67 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (!p->out_fp32 && ((p->ldo % 8) != 0 && p->N >= 32)) return fail(TTVDM_ERR_SHAPE, "gemm: ldo %% 8 != 0");
   if ((p->res1 && p->ldr1 % 8) || (p->res2 && p->ldr2 % 8)) return fail(TTVDM_ERR_SHAPE, "gemm: ldr %% 8 != 0");
 
-  const size_t smem = 2048 + (size_t)g.stages * stage_b + epi_bytes + (g.b_resident ? b_res_bytes : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  // CTA pairs (cta_group::2): each CTA stages its own 128 A rows but only HALF of the W tile, the leader issues
+  // M = 256 MMAs for both -> the L2 -> SM operand traffic per FLOP drops by a third (A + B/2 instead of A + B)
+  int pair = 0;
+  {
+    static const char* e = getenv("TTVDM_GEMM_PAIR");  // 0 = never, 1 = whenever legal, unset = heuristic
+    const bool legal = !g.b_resident && g.m_tiles >= 2 && g.block_n % 32 == 0 && (g.block_n / 2) % 8 == 0;
+    if (legal) {
+      if (e) pair = atoi(e) != 0;
+      // measured on B200 (tools/gpu_kernel_check.py --time): +5-10 % for K >= 640 with N >= 640, neutral or negative for
+      // the K = 320 / N = 320 level-0 shapes (epilogue / HBM bound)
+      else pair = (ktot_pre >= 640) && (p->N >= 640) && ((long long)g.m_tiles * g.n_tiles >= 2 * g_num_sms);
+    }
   }
   const int num_tiles = g.m_tiles * g.n_tiles;
-  const int grid = g.b_resident ? g.ctas_per_n * g.n_tiles : (num_tiles < g_num_sms ? num_tiles : g_num_sms);
-  gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
+  cudaError_t le;
+  if (pair) {
+    const int stage_pair = kABytes + (g.block_n / 2) * kBlockK * 2;
+    g.stages = (kSmemBudget - 2048 - epi_bytes) / stage_pair;
+    if (g.stages > kMaxStages) g.stages = kMaxStages;
+    const size_t smem = 2048 + (size_t)g.stages * stage_pair + epi_bytes;
+    // B tensor map: box of BN/2 rows
+    {
+      uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)p->N};
+      uint64_t str[1] = {(uint64_t)ktot * 2};
+      uint32_t box[2] = {kBlockK, (uint32_t)(g.block_n / 2)};
+      if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box))) return rc;
+    }
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e2 = cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e2 != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e2));
+      attr2 = true;
+    }
+    const int pair_tiles = ((g.m_tiles + 1) / 2) * g.n_tiles;
+    const int max_pairs = g_num_sms / 2;
+    const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    le = cudaLaunchKernelEx(&cfg, gemm_kernel<2>, tmA, tmA2, tmB, tmOut, tmRes, g);
+    if (le != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm_kernel<2>: %s", cudaGetErrorString(le));
+  } else {
+    const size_t smem = 2048 + (size_t)g.stages * stage_b + epi_bytes + (g.b_resident ? b_res_bytes : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+      if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    const int grid = g.b_resident ? g.ctas_per_n * g.n_tiles : (num_tiles < g_num_sms ? num_tiles : g_num_sms);
+    gemm_kernel<1><<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
+  }
   TTVDM_CHECK_LAUNCH("gemm_kernel");
   return 0;
 }
