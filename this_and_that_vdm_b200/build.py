@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+# debug builds only (e.g. TTVDM_EXTRA_NVCC_FLAGS=-DTTVDM_ATTN_TRACE for tools/attn_trace.py); use with --force
+NVCC_FLAGS += os.environ.get("TTVDM_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

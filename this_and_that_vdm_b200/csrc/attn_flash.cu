@@ -1,18 +1,34 @@
 // K5 / K6 / K8 — flash-style attention on tcgen05 for head_dim 64.
 //
-//   S = Q K^T   : tcgen05.mma M=128 N=128 K=64, Q/K tiles staged by TMA (128B swizzle), S in TMEM cols [0,128)
-//   softmax     : 128 threads (one query row each) read S with tcgen05.ld, online max/sum in fp32 registers,
-//                 write P (bf16) into a 128B-swizzled K-major smem tile
-//   O += P V    : tcgen05.mma M=128 N=64 K=128, V tile used in place as the MN-major B operand, O accumulates in TMEM
-//                 cols [128,192) across KV tiles; the reference max is only moved when it grows by more than 2^8
-//                 (lazy rescale), in which case the softmax warps scale their O rows in TMEM (tcgen05.ld/st).
+//   S = Q K^T   : tcgen05.mma (SS) M=128 N=128 K=16 x 4, Q/K tiles staged by TMA (128B swizzle), S_t in TMEM
+//   softmax     : 128 threads per Q tile (one query row each) pull the whole S row into registers with four
+//                 tcgen05.ld in flight, online max/sum in fp32 (four chains of 3-input max), and write P (bf16 pairs)
+//                 straight back into TMEM with tcgen05.st — P never touches shared memory
+//   O += P V    : tcgen05.mma (TS: A = P from TMEM, B = the V tile in place as MN-major smem operand) M=128 N=64 K=16
+//                 x 8, O_t accumulates in TMEM across KV tiles; the reference max is only moved when it grows by more
+//                 than 2^8 (lazy rescale), in which case the softmax warps scale their O rows in TMEM.
 //
-//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4..7 / 8..11: softmax of Q tile 0 / 1
+//   warp 0: TMA producer   warp 1 / 2: MMA issuer of Q tile 0 / 1 (warp 2 also owns the TMEM allocation)
+//   warps 4..7 / 8..11: softmax of Q tile 0 / 1
 //
-// Each CTA owns TWO 128-row Q tiles that share every K/V stage (half the K/V traffic per FLOP). Their chains
-// (softmax_t -> P_t -> [O_t += P_t V_j ; S_t = Q_t K_{j+1}^T] -> softmax_t) run out of phase, so while one tile waits
-// for its MMAs the other tile's softmax keeps the MUFU busy. 192 KB smem, 384 TMEM columns, one CTA per SM; the
-// kernel is bound by MUFU.EX2 (16/clk/SM: 1024 cycles per 128x128 tile vs 512 cycles of MMA).
+// Each CTA owns TWO 128-row Q tiles that share every K/V stage (half the K/V traffic per FLOP) and are otherwise
+// independent: own S / O / P columns, own barriers, own issuer warp. Their chains
+// (S_t(j) -> registers -> [S_t = Q_t K_{j+1}^T] -> exp2 -> P_t(j) -> [O_t += P_t(j) V_j]) overlap freely, so one tile's
+// MUFU-free phases (TMEM round trips, max, publishing P) can fall under the other tile's exponentials.
+// What bounds the kernel (measured with the clock64 event trace behind -DTTVDM_ATTN_TRACE, tools/attn_trace.py, and
+// tools/microbench/mma_rate.cu / mma_group.cu):
+//   * MUFU.EX2: 16/clk/SM = 1024 cycles per 128 x 128 tile against 512 cycles of tensor pipe (Q K^T 4 x 64, P V 8 x 32);
+//   * the ISSUING THREAD, not the tensor pipe, bounded round 1's kernel: (a) under `if (lane == 0)` ptxas wraps every
+//     tcgen05.mma in an ELECT / 4 x R2UR / branch sequence (~65 cycles per MMA, twice the cost of a 128x64x16 MMA) —
+//     under elect.sync the descriptors stay in uniform registers and MMAs issue back to back; (b) one thread is slow
+//     at everything else (an mbarrier wait is a ~130-cycle shared-memory round trip, scalar code runs at one
+//     instruction per 6-10 cycles next to two busy softmax warps), so one issuer serving both tiles spent ~800
+//     cycles per chain and forced the tiles into a fixed order; one issuer per tile with a fixed sequence of
+//     blocking waits removed that; (c) P through shared memory cost 64 KB of smem writes + reads per KV tile.
+//   Tried and measured slower on the same box: a polling scheduler over both tiles, 256-key KV tiles with two key
+//   groups per row (shared or split accumulators), refilling S registers under the exponentials (software pipelining),
+//   a forced half-phase skew between the tiles, and moving a quarter of the exp2 to an FMA-pipe polynomial.
+// 160 KB smem (Q + 4-deep K/V ring), all 512 TMEM columns, one CTA per SM.
 // The same kernel serves spatial self-attention (KV = the image's own tokens), spatial cross-attention (one KV
 // tile = the <=128 context tokens of the image's batch element) and temporal cross-attention, where the
 // reference's context-selection quirk (row (b,s) reads context (b*S+s) mod B,
@@ -28,10 +44,13 @@ constexpr int kQT = 128;      // query rows per Q tile
 constexpr int kQTiles = 2;    // Q tiles per CTA (they share every K/V tile)
 constexpr int kKT = 128;      // keys per KV tile
 constexpr int kD = 64;        // head dim
-constexpr int kKV = 3;        // K/V ring depth
+constexpr int kKV = 4;        // K/V ring depth
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kAttnThreads = 128 + 128 * kQTiles;  // 4 service warps + 4 softmax warps per Q tile
-constexpr int kAttnSmem = kTileBytes * (kQTiles + 2 * kKV + 2 * kQTiles) + 256;
+constexpr int kAttnSmem = kTileBytes * (kQTiles + 2 * kKV) + 512;
+// TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,320)  O_1 [320,384)  P_0 [384,448)  P_1 [448,512)
+constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
+
 
 enum { KV_SELF = 0, KV_CROSS_SPATIAL = 1, KV_CROSS_TEMPORAL = 2 };
 
@@ -46,8 +65,25 @@ struct AttnArgs {
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* out;
   int ldo;
+#ifdef TTVDM_ATTN_TRACE
+  long long* trace;  // [3 classes][kTraceCap] (clock << 8 | tag) event log of one CTA (debug builds only)
+#endif
 };
 
+#ifdef TTVDM_ATTN_TRACE
+constexpr int kTraceCap = 4096;
+#define TR_DECL(cls, on) long long* tr_p = (g.trace && (on) && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 2) ? g.trace + (cls) * kTraceCap : nullptr; int tr_n = 0
+#define TR(tag) do { if (tr_p && tr_n < kTraceCap) tr_p[tr_n++] = (clock64() << 8) | (tag); } while (0)
+#else
+#define TR_DECL(cls, on)
+#define TR(tag)
+#endif
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -61,8 +97,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;                                       // [kQTiles]
   uint8_t* sK = sQ + kQTiles * kTileBytes;                  // [kKV]
   uint8_t* sV = sK + kKV * kTileBytes;                      // [kKV]
-  uint8_t* sP = sV + kKV * kTileBytes;                      // [kQTiles] x (2 K-blocks of 64 keys)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kQTiles * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKV * kTileBytes);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;              // [kKV]
   uint64_t* v_full = k_full + kKV;          // [kKV]
@@ -107,8 +142,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int i = 0; i < kKV; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&k_empty[i], n_qt);  // released by the issuer of every Q tile
+      mbar_init(&v_empty[i], n_qt);
     }
     for (int i = 0; i < kQTiles; ++i) {
       mbar_init(&s_full[i], 1);
@@ -123,7 +158,6 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,320)  O_1 [320,384)
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -149,71 +183,55 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    // Per KV tile j and Q tile t:  O_t += P_t(j) V_j  as soon as the softmax warps of tile t publish P_t(j), then
-    // S_t = Q_t K_{j+1}^T straight away (S_t was consumed before P_t was published). While tile t waits for these
-    // MMAs the other tile's softmax keeps the MUFU busy; both tiles share every K/V stage.
-    const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-    const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (lane == 0) {
-      const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK), 16, 1024);
-      for (int t = 0; t < n_qt; ++t) {
-        const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + t * kTileBytes), 16, 1024);
+  } else if (warp - 1 < n_qt) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 + t drives Q tile t
+    // Per tile the events come in a fixed order (S_t(j) pulled into registers -> P_t(j) published), so each issuer runs
+    // a fixed sequence with blocking waits: S_t = Q_t K_{j+1}^T as soon as S_t(j) is in registers, O_t += P_t(j) V_j as
+    // soon as P_t(j) is published. The issuing thread is chosen with elect.sync, NOT `lane == 0` (see the header).
+    const int t = warp - 1;
+    if (elect_one()) {
+      TR_DECL(0, t == 0);
+      const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+      const uint32_t d_s = tmem_base + kColS + t * 128, d_o = tmem_base + kColO + t * 64, a_p = tmem_base + kColP + t * 64;
+      const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + t * kTileBytes), 16, 1024);
+      auto issue_qk = [&](int st) {
+        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
+        for (int k = 0; k < 4; ++k) tc_mma_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
         tc_commit(&s_full[t]);
-      }
-      tc_commit(&k_empty[0]);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_kv_tiles; ++j) {
-      const int st = j % kKV;
-      const uint32_t ph = (j / kKV) & 1;
-      const int st2 = (j + 1) % kKV;
-      const uint32_t ph2 = ((j + 1) / kKV) & 1;
-      // (a) S_t = Q_t K_{j+1}^T as soon as the softmax warps hold S_t(j) in registers: it is ready long before they
-      //     finish exponentiating tile j, so the softmax chain never waits for the tensor core
-      if (j + 1 < n_kv_tiles) {
-        mbar_wait(&k_full[st2], ph2);
-        for (int t = 0; t < n_qt; ++t) {
-          mbar_wait(&s_free[t], j & 1);
+        tc_commit(&k_empty[st]);  // one of n_qt arrivals: this tile has read K
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (n_kv_tiles > 1) mbar_wait(&k_full[1 % kKV], (1 / kKV) & 1);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        const int st = j % kKV;
+        if (j + 1 < n_kv_tiles) {
+          mbar_wait(&s_free[t], j & 1);  // the softmax warps hold S_t(j) in registers (K_{j+1} has landed: waited before)
           tc_fence_after();
-          if (lane == 0) {
-            const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + t * kTileBytes), 16, 1024);
-            const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + st2 * kTileBytes), 16, 1024);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_ss(tmem_base + t * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
-            tc_commit(&s_full[t]);
-            if (t == n_qt - 1) tc_commit(&k_empty[st2]);
-          }
-          __syncwarp();
+          TR(0x10 + t);
+          issue_qk((j + 1) % kKV);
+          TR(0x18 + t);
         }
-      }
-      // (b) O_t += P_t(j) V_j
-      mbar_wait(&v_full[st], ph);
-      for (int t = 0; t < n_qt; ++t) {
+        mbar_wait(&v_full[st], (j / kKV) & 1);  // landed long ago; this round trip hides under the softmax of tile j
         mbar_wait(&p_ready[t], j & 1);
         tc_fence_after();
-        if (lane == 0) {
-          // P_t (128 x 128, K-major, two 64-key blocks) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
-          const uint32_t sp = smem_u32(sP + t * 2 * kTileBytes);
-          const uint32_t sv = smem_u32(sV + st * kTileBytes);
+        TR(0x20 + t);
+        // P_t (128 x 128 bf16 pairs in TMEM) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
+        const uint32_t sv = smem_u32(sV + st * kTileBytes);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t p_desc = make_sdesc_sw128(sp + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024);
-            const uint64_t v_desc = make_sdesc_sw128(sv + k * 2048, 16, 1024);
-            tc_mma_ss(tmem_base + 256 + t * 64, p_desc, v_desc, idesc_pv, (j | k) != 0);
-          }
-          tc_commit(&o_done[t]);
-          if (t == n_qt - 1) tc_commit(&v_empty[st]);
-        }
-        __syncwarp();
+        for (int k = 0; k < 8; ++k)
+          tc_mma_ts(d_o, a_p + k * 8, make_sdesc_sw128(sv + k * 2048, 16, 1024), idesc_pv, (j | k) != 0);
+        tc_commit(&o_done[t]);
+        tc_commit(&v_empty[st]);  // one of n_qt arrivals
+        TR(0x28 + t);
+        if (j + 2 < n_kv_tiles) mbar_wait(&k_full[(j + 2) % kKV], ((j + 2) / kKV) & 1);
       }
     }
+    __syncwarp();
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
@@ -223,8 +241,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int r = qd * 32 + lane;   // query row within the Q tile == TMEM lane
     if (t < n_qt) {
       const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-      const uint32_t tmem_S = tmem_base + t * 128 + lane_addr;
-      const uint32_t tmem_O = tmem_base + 256 + t * 64 + lane_addr;
+      const uint32_t tmem_S = tmem_base + kColS + t * 128 + lane_addr;
+      const uint32_t tmem_O = tmem_base + kColO + t * 64 + lane_addr;
       const int q_valid = min(kQT, q_left - t * kQT);
       int my_ctx = -1;
       if (g.kv_mode == KV_CROSS_TEMPORAL) {
@@ -237,23 +255,24 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float c2 = g.scale_log2;
       float m_used = -INFINITY;  // (stale) row max the exponentials are taken against
       float l_run = 0.f;
-      uint8_t* const prow0 = sP + t * 2 * kTileBytes + r * 128;
-      const int rx = r & 7;
+      TR_DECL(1 + t, (threadIdx.x & 127) == 0);
+      const uint32_t tmem_P = tmem_base + kColP + t * 64 + lane_addr;
       for (int j = 0; j < n_kv_tiles; ++j) {
-        int kv_valid = kKT;
-        if (g.kv_mode == KV_SELF) kv_valid = min(kKT, g.seq_kv - j * kKT);
-        else kv_valid = g.seq_kv;
+        const int kv_valid = (g.kv_mode == KV_SELF) ? min(kKT, g.seq_kv - j * kKT) : g.seq_kv;
         const bool row_off = (g.kv_mode == KV_CROSS_TEMPORAL) && (my_ctx != j);
         const bool masked = (kv_valid < kKT) || (g.kv_mode == KV_CROSS_TEMPORAL);  // CTA-uniform
+        TR(1);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
+        TR(2);
         // ---- the whole S row (128 fp32) goes to registers: four tcgen05.ld in flight, one wait (~1 TMEM latency)
         uint32_t v[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + c * 32, v[c]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[t]);  // S_t(j) is in registers
+        mbar_arrive(&s_free[t]);  // S_t(j) is in registers: Q_t K_{j+1}^T may overwrite it
+        TR(3);
         if (masked) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -261,61 +280,62 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int i = 0; i < 32; ++i)
               if (row_off || c * 32 + i >= kv_valid) v[c][i] = 0xff800000u;  // -inf
         }
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains of 3-input max
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+          for (int i = 0; i < 32; i += 2)
+            mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- lazy rescale: only move the reference max when it grows by more than 2^8 (exp2 domain)
         const bool grow = (mx - m_used) * c2 > 8.0f;  // j == 0: m_used = -inf -> true (NaN if both -inf -> false)
         const float m_new = grow ? mx : m_used;
-        if (j > 0) {
-          // P_t(j-1) V_{j-1} must be complete before P_t is overwritten and before O_t is rescaled
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          // P_t(j-1) V_{j-1} must be complete before O_t is rescaled
           mbar_wait(&o_done[t], (j - 1) & 1);
           tc_fence_after();
-          if (__any_sync(0xffffffffu, grow)) {
-            const float alpha = grow ? ex2((m_used - m_new) * c2) : 1.0f;  // m_used = -inf -> 0 (row still empty)
+          const float alpha = grow ? ex2((m_used - m_new) * c2) : 1.0f;  // m_used = -inf -> 0 (row still empty)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[32];
-              tmem_ld_32x32(tmem_O + c * 32, o);
-              tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_O + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32(tmem_O + c * 32, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tmem_O + c * 32, o);
           }
+          tmem_st_wait();
+          l_run *= alpha;
         }
         m_used = m_new;
         const float ms = (m_used == -INFINITY) ? 0.f : m_used * c2;
-        // ---- probabilities -> 128B-swizzled smem tile (bf16), row sum
+        TR(4);
+        // ---- probabilities: bf16 pairs (P column c = keys 2c, 2c+1), row sum
         float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2(fmaf(__uint_as_float(v[c][i]), c2, -ms));  // exp2(-inf) = 0 for masked keys
             const float p1 = ex2(fmaf(__uint_as_float(v[c][i + 1]), c2, -ms));
             sum0 += p0;
             sum1 += p1;
-            pk[i >> 1] = pack_bf16(p0, p1);
+            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
           }
-          // keys [c*32, c*32+32) live in K-block (c>>1), 16-byte chunks ((c&1)*4 .. +3), XOR-swizzled by (row & 7)
-          uint8_t* prow = prow0 + (c >> 1) * kTileBytes;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int chunk = ((c & 1) * 4 + ch) ^ rx;
-            *reinterpret_cast<uint4*>(prow + chunk * 16) =
-                make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-          }
-        }
         l_run += sum0 + sum1;
-        fence_async_smem();
+        TR(5);
+        if (j > 0) {
+          // the tensor core must have finished reading P_t(j-1) (issued one tile ago)
+          mbar_wait(&o_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_32x32(tmem_P, pk[0]);
+        tmem_st_32x32(tmem_P + 32, pk[1]);
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[t]);
+        TR(6);
       }
       // ---- epilogue: O / l
       mbar_wait(&o_done[t], (n_kv_tiles - 1) & 1);
@@ -398,6 +418,9 @@ extern "C" int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream_) {
   g.scale_log2 = p->scale * 1.4426950408889634f;
   g.out = static_cast<__nv_bfloat16*>(p->out);
   g.ldo = p->ldo;
+#ifdef TTVDM_ATTN_TRACE
+  { const char* e = getenv("TTVDM_ATTN_TRACE"); g.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 10)) : nullptr; }
+#endif
   const long long rows = (long long)p->n_img * p->seq;
   return launch_attn(p->q, p->ldq, rows, p->k, p->ldk, p->v, p->ldv, rows, g, p->n_img,
                      static_cast<cudaStream_t>(stream_));

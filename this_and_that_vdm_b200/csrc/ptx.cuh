@@ -47,6 +47,43 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (no suspend-time hint): for schedulers that poll several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// six independent probes in flight at once (one shared-memory latency instead of six); bit i = barrier i's phase done
+__device__ __forceinline__ uint32_t mbar_test_wait6(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2,
+                                                    uint32_t p2, uint64_t* b3, uint32_t p3, uint64_t* b4, uint32_t p4,
+                                                    uint64_t* b5, uint32_t p5) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred Q0, Q1, Q2, Q3, Q4, Q5;\n\t.reg .b32 x;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q0, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q1, [%3], %4;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q2, [%5], %6;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q3, [%7], %8;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q4, [%9], %10;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 Q5, [%11], %12;\n\t"
+      "selp.b32 %0, 1, 0, Q0;\n\t"
+      "selp.b32 x, 2, 0, Q1;\n\tor.b32 %0, %0, x;\n\t"
+      "selp.b32 x, 4, 0, Q2;\n\tor.b32 %0, %0, x;\n\t"
+      "selp.b32 x, 8, 0, Q3;\n\tor.b32 %0, %0, x;\n\t"
+      "selp.b32 x, 16, 0, Q4;\n\tor.b32 %0, %0, x;\n\t"
+      "selp.b32 x, 32, 0, Q5;\n\tor.b32 %0, %0, x;\n\t}\n"
+      : "=r"(r)
+      : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1), "r"(smem_u32(b2)), "r"(p2), "r"(smem_u32(b3)), "r"(p3),
+        "r"(smem_u32(b4)), "r"(p4), "r"(smem_u32(b5)), "r"(p5)
+      : "memory");
+  return r;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
