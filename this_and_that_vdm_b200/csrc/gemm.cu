@@ -309,9 +309,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // one thread, chosen with elect.sync (NOT `lane == 0`: only then does ptxas keep tensor-map / descriptor operands in
+    // uniform registers instead of wrapping every TMA / MMA instruction in an ELECT + R2UR + branch sequence)
+    if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
-    if (g.b_resident && lane == 0) {
+    if (g.b_resident) {
       // the CTA's N tile of W: all K chunks, once
       const int n0 = (blockIdx.x % g.n_tiles) * g.block_n;
       mbar_expect_tx(bres_bar, num_kc * b_chunk_bytes);
@@ -323,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const TileCoord t = tile_coord(g, tile);
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (lane == 0) {
+        {
           uint8_t* sa = tiles + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           if (kCtas == 1) mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
@@ -346,15 +349,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (kCtas == 2) tma_load_2d_pair(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0 + cta_rank * (g.block_n >> 1));
           else if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
         }
-        __syncwarp();
         if (++stage == g.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp == 1 && cta_rank == 0) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair)
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair), one elected thread
+    if (elect_one()) {
     const uint32_t idesc = make_idesc_bf16(kBlockM * kCtas, g.block_n);
     int stage = 0;
     uint32_t phase = 0;
@@ -371,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kc = 0; kc < num_kc; ++kc) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
           const uint32_t sb = g.b_resident ? smem_u32(bres + kc * b_chunk_bytes) : sa + kABytes;
           const uint64_t a_desc = make_sdesc_sw128(sa, 16, 1024);
@@ -390,13 +395,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (kc == num_kc - 1) tc_commit_pair(&tfull_bar[acc]);
           }
         }
-        __syncwarp();
         if (++stage == g.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;           // TMEM lane quarter this warp may access
