@@ -43,12 +43,18 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double*
     float sm[8], sq[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm[i] = sq[i] = 0.f;
-    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
-      uint4 u[4];
+    // 4 independent 16-byte loads per thread and step, and the next step's loads are issued before the current
+    // step's arithmetic (8 loads in flight): the kernel is latency-bound otherwise
+    auto load4 = [&](uint4 (&u)[4], int r) {
 #pragma unroll
-      for (int b = 0; b < 4; ++b)  // 4 independent 16-byte loads in flight per thread
+      for (int b = 0; b < 4; ++b)
         u[b] = (r + b * rpi < r1) ? __ldg(reinterpret_cast<const uint4*>(s.x + (base + r + b * rpi) * s.ld) + col)
                                   : make_uint4(0, 0, 0, 0);
+    };
+    uint4 u[4], un[4];
+    load4(u, r0 + rofs);
+    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
+      load4(un, r + 4 * rpi);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         float f[8];
@@ -59,6 +65,8 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double*
           sq[i] += f[i] * f[i];
         }
       }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) u[b] = un[b];
     }
     const int c0 = s.c_off + col * 8;
     // merge the (at most few) groups this vector touches before going to shared memory
@@ -119,12 +127,16 @@ gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const d
       ka[i] = s_rstd[gi] * gamma[c0 + i];
       kb[i] = beta[c0 + i] - s_mean[gi] * ka[i];
     }
-    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
-      uint4 u[4];
+    auto load4 = [&](uint4 (&u)[4], int r) {
 #pragma unroll
       for (int b = 0; b < 4; ++b)
         u[b] = (r + b * rpi < r1) ? __ldg(reinterpret_cast<const uint4*>(s.x + (base + r + b * rpi) * s.ld) + col)
                                   : make_uint4(0, 0, 0, 0);
+    };
+    uint4 u[4], un[4];
+    load4(u, r0 + rofs);
+    for (int r = r0 + rofs; r < r1; r += 4 * rpi) {
+      load4(un, r + 4 * rpi);  // next step's loads are in flight while this step is normalised and stored
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         if (r + b * rpi >= r1) break;
@@ -139,6 +151,8 @@ gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const d
         *reinterpret_cast<uint4*>(out + (base + r + b * rpi) * ldo + c0) =
             make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
       }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) u[b] = un[b];
     }
   }
 }
@@ -207,6 +221,92 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, i
   }
 }
 
+// Vectorised variant for the channel counts of the SVD transformers (C = 40 * kLanes: 320 / 640 / 1280): kLanes lanes
+// share a row, each lane owns five 16-byte vectors (lane l reads vectors l, l + kLanes, ...: every access of the lane
+// group is a contiguous 128-byte line or more), 32 / kLanes rows per warp. Same arithmetic order per element as
+// layernorm_kernel up to the reduction tree.
+template <int kLanes>
+__global__ void layernorm_vec_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, const float* __restrict__ addvec,
+                                     int F, int S, __nv_bfloat16* __restrict__ sum_out, int ldsum,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     __nv_bfloat16* __restrict__ out, int ldo) {
+  constexpr int kC = 40 * kLanes;
+  constexpr int kRowsPerWarp = 32 / kLanes;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % kLanes;
+  const long long row = (long long)warp * kRowsPerWarp + lane / kLanes;
+  const bool live = row < rows;  // whole lane groups are live or not; dead groups still take part in the shuffles
+  float v[5][8];
+  float s = 0.f;
+  if (live) {
+    const float* av = (addvec != nullptr) ? addvec + (size_t)((row / S) % F) * kC : nullptr;
+    uint4 raw[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) raw[i] = *reinterpret_cast<const uint4*>(x + row * ldx + (sub + i * kLanes) * 8);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(w[k]);
+        v[i][2 * k] = f.x;
+        v[i][2 * k + 1] = f.y;
+      }
+      if (av != nullptr) {
+        const float4 e0 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8);
+        const float4 e1 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8 + 4);
+        v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
+        v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
+        if (sum_out != nullptr) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            pk[k] = pack_bf16(v[i][2 * k], v[i][2 * k + 1]);
+            const float2 f = unpack_bf16(pk[k]);  // normalise exactly what downstream residuals will read
+            v[i][2 * k] = f.x;
+            v[i][2 * k + 1] = f.y;
+          }
+          *reinterpret_cast<uint4*>(sum_out + row * ldsum + (sub + i * kLanes) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[i][k];
+    }
+  }
+#pragma unroll
+  for (int o = kLanes / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / kC;
+  float ss = 0.f;
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        ss += d * d;
+      }
+  }
+#pragma unroll
+  for (int o = kLanes / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (!live) return;
+  const float rstd = rsqrtf(ss / kC + eps);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c0 = (sub + i * kLanes) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      pk[k] = pack_bf16((v[i][2 * k] - mean) * rstd * gg[2 * k] + bb[2 * k],
+                        (v[i][2 * k + 1] - mean) * rstd * gg[2 * k + 1] + bb[2 * k + 1]);
+    *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 }  // namespace ttvdm
 
 using namespace ttvdm;
@@ -224,11 +324,18 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   if (p->rows <= 0 || p->rows_per_inst <= 0 || p->rows % p->rows_per_inst != 0)
     return fail(TTVDM_ERR_SHAPE, "groupnorm: rows=%d rows_per_inst=%d", p->rows, p->rows_per_inst);
   const int n_inst = p->rows / p->rows_per_inst;
-  // chunk depends on rows_per_inst only (not on how many sequences this rank holds): the fp32 partial sums, and so
-  // the statistics, are identical for a sharded half-pair and the whole pair
-  int rows_per_cta = p->rows_per_inst / 64;
-  if (rows_per_cta < 8) rows_per_cta = 8;
-  if (rows_per_cta > 64) rows_per_cta = 64;
+  // The chunking depends on rows_per_inst and the channel counts only (not on how many sequences this rank holds):
+  // the fp32 partial sums, and so the statistics, are identical for a sharded half-pair and the whole pair.
+  // A CTA walks its rows in steps of `granule` = 4 * (512 / vectors per row) rows; it gets 4..8 whole steps (setup —
+  // group statistics, affine coefficients — is ~200 instructions per thread and must be amortised; too many rows per
+  // CTA would leave the 5-D temporal norms with fewer CTAs than SMs).
+  const int vmax0 = (p->c1 > c2 ? p->c1 : c2) / 8;  // >= 1 (channels are multiples of 8, C % 32 == 0)
+  const int granule = 4 * (vmax0 < 512 ? 512 / vmax0 : 1);
+  int steps = (p->rows_per_inst + 48 * granule - 1) / (48 * granule);
+  if (steps < 4) steps = 4;
+  if (steps > 8) steps = 8;
+  int rows_per_cta = granule * steps;
+  if (rows_per_cta > p->rows_per_inst) rows_per_cta = p->rows_per_inst;
   const int chunks = (p->rows_per_inst + rows_per_cta - 1) / rows_per_cta;
   cudaError_t e = cudaMemsetAsync(p->stats, 0, (size_t)n_inst * 64 * sizeof(double), stream);
   if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "groupnorm: memset: %s", cudaGetErrorString(e));
@@ -262,6 +369,27 @@ extern "C" int ttvdm_layernorm(const ttvdm_layernorm_params* p, void* stream_) {
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p->x);
   __nv_bfloat16* so = static_cast<__nv_bfloat16*>(p->sum_out);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p->out);
+  // 16-byte-vector kernel for C = 320 / 640 / 1280 when every row is 16-byte aligned
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(o) % 16 == 0) &&
+                       (p->ldx % 8 == 0) && (p->ldo % 8 == 0) &&
+                       (!so || (reinterpret_cast<uintptr_t>(so) % 16 == 0 && p->ldsum % 8 == 0)) &&
+                       (!p->addvec || reinterpret_cast<uintptr_t>(p->addvec) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p->gamma) % 16 == 0) && (reinterpret_cast<uintptr_t>(p->beta) % 16 == 0);
+  if (aligned && (p->C == 320 || p->C == 640 || p->C == 1280)) {
+    const int lanes = p->C / 40;
+    const int rows_per_warp = 32 / lanes;
+    const int warps = (p->rows + rows_per_warp - 1) / rows_per_warp;
+    const int vgrid = (warps + (threads / 32) - 1) / (threads / 32);
+#define LNV_LAUNCH(L)                                                                                                \
+  layernorm_vec_kernel<L><<<vgrid, threads, 0, stream>>>(x, p->ldx, p->rows, p->addvec, p->F, p->S, so, p->ldsum, p->gamma, \
+                                                         p->beta, p->eps, o, p->ldo)
+    if (lanes == 8) LNV_LAUNCH(8);
+    else if (lanes == 16) LNV_LAUNCH(16);
+    else LNV_LAUNCH(32);
+#undef LNV_LAUNCH
+    TTVDM_CHECK_LAUNCH("layernorm_vec_kernel");
+    return 0;
+  }
 #define LN_LAUNCH(PPL)                                                                                             \
   layernorm_kernel<PPL><<<grid, threads, 0, stream>>>(x, p->ldx, p->rows, p->C, p->addvec, p->F, p->S, so, p->ldsum, \
                                                       p->gamma, p->beta, p->eps, o, p->ldo)
