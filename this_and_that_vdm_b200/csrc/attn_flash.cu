@@ -28,7 +28,7 @@
 //   Tried and measured slower on the same box: a polling scheduler over both tiles, 256-key KV tiles with two key
 //   groups per row (shared or split accumulators), refilling S registers under the exponentials (software pipelining),
 //   a forced half-phase skew between the tiles, and moving a quarter of the exp2 to an FMA-pipe polynomial.
-// 160 KB smem (Q + 4-deep K/V ring), all 512 TMEM columns, one CTA per SM.
+// 192 KB smem (two Q buffers + 4-deep K/V ring), all 512 TMEM columns, one persistent CTA per SM (see the kernel).
 // The same kernel serves spatial self-attention (KV = the image's own tokens), spatial cross-attention (one KV
 // tile = the <=128 context tokens of the image's batch element) and temporal cross-attention, where the
 // reference's context-selection quirk (row (b,s) reads context (b*S+s) mod B,
@@ -47,7 +47,7 @@ constexpr int kD = 64;        // head dim
 constexpr int kKV = 4;        // K/V ring depth
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kAttnThreads = 128 + 128 * kQTiles;  // 4 service warps + 4 softmax warps per Q tile
-constexpr int kAttnSmem = kTileBytes * (kQTiles + 2 * kKV) + 512;
+constexpr int kAttnSmem = kTileBytes * (2 * kQTiles + 2 * kKV) + 512;
 // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,320)  O_1 [320,384)  P_0 [384,448)  P_1 [448,512)
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 
@@ -58,8 +58,9 @@ struct AttnArgs {
   int kv_mode;
   int seq_q;      // query rows per unit (image)
   int seq_kv;     // SELF: keys per unit; CROSS: L
-  int q_tiles;    // CTAs per (unit, head) = ceil(seq_q / 256)
+  int q_tiles;    // work items per (unit, head) = ceil(seq_q / 256)
   int heads;
+  int units;      // images (SELF) / (b, f) pairs (CROSS)
   int F, S;       // rows ordered (b, f, s); unit = (b, f)
   int n_ctx, batch_offset;
   float scale_log2;  // scale * log2(e)
@@ -72,7 +73,7 @@ struct AttnArgs {
 
 #ifdef TTVDM_ATTN_TRACE
 constexpr int kTraceCap = 4096;
-#define TR_DECL(cls, on) long long* tr_p = (g.trace && (on) && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 2) ? g.trace + (cls) * kTraceCap : nullptr; int tr_n = 0
+#define TR_DECL(cls, on) long long* tr_p = (g.trace && (on) && blockIdx.x == 3) ? g.trace + (cls) * kTraceCap : nullptr; int tr_n = 0
 #define TR(tag) do { if (tr_p && tr_n < kTraceCap) tr_p[tr_n++] = (clock64() << 8) | (tag); } while (0)
 #else
 #define TR_DECL(cls, on)
@@ -94,43 +95,56 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                       // [kQTiles]
-  uint8_t* sK = sQ + kQTiles * kTileBytes;                  // [kKV]
+  uint8_t* sQ = smem;                                       // [2 buffers][kQTiles]
+  uint8_t* sK = sQ + 2 * kQTiles * kTileBytes;              // [kKV]
   uint8_t* sV = sK + kKV * kTileBytes;                      // [kKV]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKV * kTileBytes);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;              // [kKV]
+  uint64_t* q_full = bars + 0;              // [2]        the Q tiles of a work item have landed
+  uint64_t* q_empty = q_full + 2;           // [2]        both issuers are done with the Q buffer
+  uint64_t* k_full = q_empty + 2;           // [kKV]
   uint64_t* v_full = k_full + kKV;          // [kKV]
-  uint64_t* k_empty = v_full + kKV;         // [kKV]
+  uint64_t* k_empty = v_full + kKV;         // [kKV]      released by the issuer of every Q tile
   uint64_t* v_empty = k_empty + kKV;        // [kKV]
   uint64_t* s_full = v_empty + kKV;         // [kQTiles]  S_t = Q_t K_j^T is in TMEM
-  uint64_t* p_ready = s_full + kQTiles;     // [kQTiles]  P_t written (and S_t consumed) by the softmax warps of tile t
+  uint64_t* p_ready = s_full + kQTiles;     // [kQTiles]  P_t written by the softmax warps of tile t
   uint64_t* o_done = p_ready + kQTiles;     // [kQTiles]  O_t += P_t V_j complete
   uint64_t* s_free = o_done + kQTiles;      // [kQTiles]  S_t copied to registers: the next Q_t K^T may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + kQTiles);
+  uint64_t* o_free = s_free + kQTiles;      // [kQTiles]  O_t of the finished work item is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + kQTiles);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  // ---- which tiles am I
-  const int qt = blockIdx.x;
-  const int head = blockIdx.y;
-  const int unit = blockIdx.z;
-  const int q_row0 = unit * g.seq_q + qt * (kQT * kQTiles);  // global query row of Q tile 0, row 0
-  const int q_left = g.seq_q - qt * (kQT * kQTiles);          // valid query rows in this CTA (> 0)
-  const int n_qt = q_left > kQT ? 2 : 1;                      // Q tiles that carry at least one valid row
-  int n_kv_tiles, kv_row_base;
-  if (g.kv_mode == KV_SELF) {
-    n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
-    kv_row_base = unit * g.seq_kv;
-  } else if (g.kv_mode == KV_CROSS_SPATIAL) {
-    n_kv_tiles = 1;
-    kv_row_base = (g.batch_offset + unit / g.F) * g.seq_kv;
-  } else {
-    n_kv_tiles = g.n_ctx;
-    kv_row_base = 0;
-  }
+  // ---- persistent CTA: work item w = (q tile pair, head, unit), w = blockIdx.x, blockIdx.x + gridDim.x, ...
+  // Barriers, TMEM and the pipeline state live across work items (all parities come from running counters), so the
+  // next item's Q/K/V loads and its first Q K^T overlap the previous item's last P V and its output stores. This is
+  // what makes the cross-attention calls (ONE KV tile per item) and the low-resolution levels efficient: with one
+  // CTA per item they paid ~5 us of set-up and exposed latency per ~1 us of work.
+  const int total_works = g.q_tiles * g.heads * g.units;
+  struct Work {
+    int q_row0, q_left, head, n_kv_tiles, kv_row_base;
+  };
+  auto decode = [&](int w) -> Work {
+    Work k;
+    const int qt = w % g.q_tiles;
+    const int hu = w / g.q_tiles;
+    k.head = hu % g.heads;
+    const int unit = hu / g.heads;
+    k.q_row0 = unit * g.seq_q + qt * (kQT * kQTiles);  // global query row of Q tile 0, row 0
+    k.q_left = g.seq_q - qt * (kQT * kQTiles);          // valid query rows of this item (> 0)
+    if (g.kv_mode == KV_SELF) {
+      k.n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
+      k.kv_row_base = unit * g.seq_kv;
+    } else if (g.kv_mode == KV_CROSS_SPATIAL) {
+      k.n_kv_tiles = 1;
+      k.kv_row_base = (g.batch_offset + unit / g.F) * g.seq_kv;
+    } else {
+      k.n_kv_tiles = g.n_ctx;
+      k.kv_row_base = 0;
+    }
+    return k;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -138,18 +152,22 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tma_prefetch_desc(&tmV);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], kQTiles);
+    }
     for (int i = 0; i < kKV; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], n_qt);  // released by the issuer of every Q tile
-      mbar_init(&v_empty[i], n_qt);
+      mbar_init(&k_empty[i], kQTiles);
+      mbar_init(&v_empty[i], kQTiles);
     }
     for (int i = 0; i < kQTiles; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
       mbar_init(&s_free[i], 128);
+      mbar_init(&o_free[i], 128);
     }
     mbar_fence_init();
   }
@@ -162,28 +180,34 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, n_qt * kTileBytes);
-      for (int t = 0; t < n_qt; ++t) tma_load_2d(sQ + t * kTileBytes, &tmQ, q_full, head * kD, q_row0 + t * kQT);
-    }
-    for (int j = 0; j < n_kv_tiles; ++j) {
-      const int st = j % kKV;
-      const uint32_t ph = (j / kKV) & 1;
-      const int kv_row = (g.kv_mode == KV_CROSS_TEMPORAL) ? j * g.seq_kv : kv_row_base + j * kKT;
-      mbar_wait(&k_empty[st], ph ^ 1);
-      if (lane == 0) {
-        mbar_expect_tx(&k_full[st], kTileBytes);
-        tma_load_2d(sK + st * kTileBytes, &tmK, &k_full[st], head * kD, kv_row);
+    // ------------------------------------------------------------------ TMA producer (one elected thread)
+    if (elect_one()) {
+      uint32_t kt = 0;  // K/V tiles loaded so far (ring position)
+      int wi = 0;
+      for (int w = blockIdx.x; w < total_works; w += gridDim.x, ++wi) {
+        const Work k = decode(w);
+        const int qb = wi & 1;
+        mbar_wait(&q_empty[qb], ((wi >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], kQTiles * kTileBytes);
+        // both Q tiles are always loaded: a tile past the item's rows holds the next image's rows or TMA zero fill
+        // and is computed but never stored
+        for (int t = 0; t < kQTiles; ++t)
+          tma_load_2d(sQ + (qb * kQTiles + t) * kTileBytes, &tmQ, &q_full[qb], k.head * kD, k.q_row0 + t * kQT);
+        for (int j = 0; j < k.n_kv_tiles; ++j, ++kt) {
+          const int st = kt % kKV;
+          const uint32_t ph = (kt / kKV) & 1;
+          const int kv_row = (g.kv_mode == KV_CROSS_TEMPORAL) ? j * g.seq_kv : k.kv_row_base + j * kKT;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], kTileBytes);
+          tma_load_2d(sK + st * kTileBytes, &tmK, &k_full[st], k.head * kD, kv_row);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], kTileBytes);
+          tma_load_2d(sV + st * kTileBytes, &tmV, &v_full[st], k.head * kD, kv_row);
+        }
       }
-      mbar_wait(&v_empty[st], ph ^ 1);
-      if (lane == 0) {
-        mbar_expect_tx(&v_full[st], kTileBytes);
-        tma_load_2d(sV + st * kTileBytes, &tmV, &v_full[st], head * kD, kv_row);
-      }
-      __syncwarp();
     }
-  } else if (warp - 1 < n_qt) {
+    __syncwarp();
+  } else if (warp - 1 < kQTiles) {
     // ------------------------------------------------------------------ MMA issuers: warp 1 + t drives Q tile t
     // Per tile the events come in a fixed order (S_t(j) pulled into registers -> P_t(j) published), so each issuer runs
     // a fixed sequence with blocking waits: S_t = Q_t K_{j+1}^T as soon as S_t(j) is in registers, O_t += P_t(j) V_j as
@@ -194,41 +218,56 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
       const uint32_t d_s = tmem_base + kColS + t * 128, d_o = tmem_base + kColO + t * 64, a_p = tmem_base + kColP + t * 64;
-      const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + t * kTileBytes), 16, 1024);
-      auto issue_qk = [&](int st) {
-        const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
+      uint32_t kt = 0;  // K/V tiles consumed before this work item (ring position)
+      uint32_t c = 0;   // KV tiles this Q tile has been through (parity of s_full / s_free / p_ready / o_done)
+      int wi = 0;
+      for (int w = blockIdx.x; w < total_works; w += gridDim.x, ++wi) {
+        const Work k = decode(w);
+        const int qb = wi & 1;
+        const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ + (qb * kQTiles + t) * kTileBytes), 16, 1024);
+        auto issue_qk = [&](uint32_t tile) {
+          const int st = tile % kKV;
+          const uint64_t k_desc = make_sdesc_sw128(smem_u32(sK + st * kTileBytes), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_ss(d_s, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k != 0);
-        tc_commit(&s_full[t]);
-        tc_commit(&k_empty[st]);  // one of n_qt arrivals: this tile has read K
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0);
-      if (n_kv_tiles > 1) mbar_wait(&k_full[1 % kKV], (1 / kKV) & 1);
-      for (int j = 0; j < n_kv_tiles; ++j) {
-        const int st = j % kKV;
-        if (j + 1 < n_kv_tiles) {
-          mbar_wait(&s_free[t], j & 1);  // the softmax warps hold S_t(j) in registers (K_{j+1} has landed: waited before)
-          tc_fence_after();
-          TR(0x10 + t);
-          issue_qk((j + 1) % kKV);
-          TR(0x18 + t);
-        }
-        mbar_wait(&v_full[st], (j / kKV) & 1);  // landed long ago; this round trip hides under the softmax of tile j
-        mbar_wait(&p_ready[t], j & 1);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_ss(d_s, q_desc + 2 * kk, k_desc + 2 * kk, idesc_qk, kk != 0);
+          tc_commit(&s_full[t]);
+          tc_commit(&k_empty[st]);  // one of kQTiles arrivals: this tile has read K
+        };
+        mbar_wait(&q_full[qb], (wi >> 1) & 1);
+        mbar_wait(&k_full[kt % kKV], (kt / kKV) & 1);
+        if (c > 0) mbar_wait(&s_free[t], (c - 1) & 1);  // S_t of the previous item's last tile is in registers
         tc_fence_after();
-        TR(0x20 + t);
-        // P_t (128 x 128 bf16 pairs in TMEM) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
-        const uint32_t sv = smem_u32(sV + st * kTileBytes);
+        issue_qk(kt);
+        if (k.n_kv_tiles == 1) tc_commit(&q_empty[qb]);
+        else mbar_wait(&k_full[(kt + 1) % kKV], ((kt + 1) / kKV) & 1);
+        for (int j = 0; j < k.n_kv_tiles; ++j) {
+          const uint32_t tile = kt + j;
+          const int st = tile % kKV;
+          if (j + 1 < k.n_kv_tiles) {
+            mbar_wait(&s_free[t], (c + j) & 1);  // the softmax warps hold S_t(j) in registers (K_{j+1} has landed)
+            tc_fence_after();
+            TR(0x10 + t);
+            issue_qk(tile + 1);
+            if (j + 2 == k.n_kv_tiles) tc_commit(&q_empty[qb]);  // last Q K^T of the item: one of kQTiles arrivals
+            TR(0x18 + t);
+          }
+          mbar_wait(&v_full[st], (tile / kKV) & 1);  // landed long ago; this round trip hides under the softmax
+          mbar_wait(&p_ready[t], (c + j) & 1);
+          if (j == 0 && wi > 0) mbar_wait(&o_free[t], (wi - 1) & 1);  // the previous item's O_t has been read out
+          tc_fence_after();
+          TR(0x20 + t);
+          // P_t (128 x 128 bf16 pairs in TMEM) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
+          const uint32_t sv = smem_u32(sV + st * kTileBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          tc_mma_ts(d_o, a_p + k * 8, make_sdesc_sw128(sv + k * 2048, 16, 1024), idesc_pv, (j | k) != 0);
-        tc_commit(&o_done[t]);
-        tc_commit(&v_empty[st]);  // one of n_qt arrivals
-        TR(0x28 + t);
-        if (j + 2 < n_kv_tiles) mbar_wait(&k_full[(j + 2) % kKV], ((j + 2) / kKV) & 1);
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_ts(d_o, a_p + kk * 8, make_sdesc_sw128(sv + kk * 2048, 16, 1024), idesc_pv, (j | kk) != 0);
+          tc_commit(&o_done[t]);
+          tc_commit(&v_empty[st]);  // one of kQTiles arrivals
+          TR(0x28 + t);
+          if (j + 2 < k.n_kv_tiles) mbar_wait(&k_full[(tile + 2) % kKV], ((tile + 2) / kKV) & 1);
+        }
+        kt += k.n_kv_tiles;
+        c += k.n_kv_tiles;
       }
     }
     __syncwarp();
@@ -239,70 +278,72 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int t = (warp - 4) >> 2;  // Q tile of this warp
     const int qd = warp & 3;        // TMEM lane quarter
     const int r = qd * 32 + lane;   // query row within the Q tile == TMEM lane
-    if (t < n_qt) {
-      const uint32_t lane_addr = uint32_t(qd * 32) << 16;
-      const uint32_t tmem_S = tmem_base + kColS + t * 128 + lane_addr;
-      const uint32_t tmem_O = tmem_base + kColO + t * 64 + lane_addr;
-      const int q_valid = min(kQT, q_left - t * kQT);
+    const uint32_t lane_addr = uint32_t(qd * 32) << 16;
+    const uint32_t tmem_S = tmem_base + kColS + t * 128 + lane_addr;
+    const uint32_t tmem_O = tmem_base + kColO + t * 64 + lane_addr;
+    const uint32_t tmem_P = tmem_base + kColP + t * 64 + lane_addr;
+    const float c2 = g.scale_log2;
+    uint32_t c = 0;  // KV tiles this Q tile has been through
+    TR_DECL(1 + t, (threadIdx.x & 127) == 0);
+    for (int w = blockIdx.x; w < total_works; w += gridDim.x) {
+      const Work k = decode(w);
+      const int q_valid = min(kQT, k.q_left - t * kQT);  // <= 0: this tile carries no row of the item
       int my_ctx = -1;
       if (g.kv_mode == KV_CROSS_TEMPORAL) {
         // global row -> (b, f, s); temporal batch row (b, s) reads context (b*S + s) mod n_ctx  [reference quirk]
-        const long long row = (long long)q_row0 + t * kQT + r;
+        const long long row = (long long)k.q_row0 + t * kQT + r;
         const int s = (int)(row % g.S);
         const int b = (int)(row / ((long long)g.F * g.S)) + g.batch_offset;
         my_ctx = (int)(((long long)b * g.S + s) % g.n_ctx);
       }
-      const float c2 = g.scale_log2;
       float m_used = -INFINITY;  // (stale) row max the exponentials are taken against
       float l_run = 0.f;
-      TR_DECL(1 + t, (threadIdx.x & 127) == 0);
-      const uint32_t tmem_P = tmem_base + kColP + t * 64 + lane_addr;
-      for (int j = 0; j < n_kv_tiles; ++j) {
+      for (int j = 0; j < k.n_kv_tiles; ++j, ++c) {
         const int kv_valid = (g.kv_mode == KV_SELF) ? min(kKT, g.seq_kv - j * kKT) : g.seq_kv;
         const bool row_off = (g.kv_mode == KV_CROSS_TEMPORAL) && (my_ctx != j);
         const bool masked = (kv_valid < kKT) || (g.kv_mode == KV_CROSS_TEMPORAL);  // CTA-uniform
         TR(1);
-        mbar_wait(&s_full[t], j & 1);
+        mbar_wait(&s_full[t], c & 1);
         tc_fence_after();
         TR(2);
         // ---- the whole S row (128 fp32) goes to registers: four tcgen05.ld in flight, one wait (~1 TMEM latency)
         uint32_t v[4][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + c * 32, v[c]);
+        for (int cc = 0; cc < 4; ++cc) tmem_ld_32x32(tmem_S + cc * 32, v[cc]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[t]);  // S_t(j) is in registers: Q_t K_{j+1}^T may overwrite it
+        mbar_arrive(&s_free[t]);  // S_t(j) is in registers: the next Q_t K^T may overwrite it
         TR(3);
         if (masked) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (row_off || c * 32 + i >= kv_valid) v[c][i] = 0xff800000u;  // -inf
+              if (row_off || cc * 32 + i >= kv_valid) v[cc][i] = 0xff800000u;  // -inf
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains of 3-input max
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
-            mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+            mx4[(i >> 1) & 3] = fmax3(mx4[(i >> 1) & 3], __uint_as_float(v[cc][i]), __uint_as_float(v[cc][i + 1]));
         const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // ---- lazy rescale: only move the reference max when it grows by more than 2^8 (exp2 domain)
         const bool grow = (mx - m_used) * c2 > 8.0f;  // j == 0: m_used = -inf -> true (NaN if both -inf -> false)
         const float m_new = grow ? mx : m_used;
         if (j > 0 && __any_sync(0xffffffffu, grow)) {
           // P_t(j-1) V_{j-1} must be complete before O_t is rescaled
-          mbar_wait(&o_done[t], (j - 1) & 1);
+          mbar_wait(&o_done[t], (c - 1) & 1);
           tc_fence_after();
           const float alpha = grow ? ex2((m_used - m_new) * c2) : 1.0f;  // m_used = -inf -> 0 (row still empty)
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int cc = 0; cc < 2; ++cc) {
             uint32_t o[32];
-            tmem_ld_32x32(tmem_O + c * 32, o);
+            tmem_ld_32x32(tmem_O + cc * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tmem_O + c * 32, o);
+            tmem_st_32x32(tmem_O + cc * 32, o);
           }
           tmem_st_wait();
           l_run *= alpha;
@@ -314,20 +355,21 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float sum0 = 0.f, sum1 = 0.f;
         uint32_t pk[2][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[c][i]), c2, -ms));  // exp2(-inf) = 0 for masked keys
-            const float p1 = ex2(fmaf(__uint_as_float(v[c][i + 1]), c2, -ms));
+            const float p0 = ex2(fmaf(__uint_as_float(v[cc][i]), c2, -ms));  // exp2(-inf) = 0 for masked keys
+            const float p1 = ex2(fmaf(__uint_as_float(v[cc][i + 1]), c2, -ms));
             sum0 += p0;
             sum1 += p1;
-            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+            pk[cc >> 1][(cc & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
           }
         l_run += sum0 + sum1;
         TR(5);
         if (j > 0) {
-          // the tensor core must have finished reading P_t(j-1) (issued one tile ago)
-          mbar_wait(&o_done[t], (j - 1) & 1);
+          // the tensor core must have finished reading P_t(j-1) (issued one tile ago); for j == 0 the previous item's
+          // epilogue below has already waited for its last P V
+          mbar_wait(&o_done[t], (c - 1) & 1);
           tc_fence_after();
         }
         tmem_st_32x32(tmem_P, pk[0]);
@@ -338,25 +380,27 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         TR(6);
       }
       // ---- epilogue: O / l
-      mbar_wait(&o_done[t], (n_kv_tiles - 1) & 1);
+      mbar_wait(&o_done[t], (c - 1) & 1);
       tc_fence_after();
       const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
-      __nv_bfloat16* orow = g.out + (long long)(q_row0 + t * kQT + r) * g.ldo + head * kD;
+      uint32_t o[2][32];
+      tmem_ld_32x32(tmem_O, o[0]);
+      tmem_ld_32x32(tmem_O + 32, o[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_free[t]);  // O_t is in registers: the next item's first P V may overwrite it
+      if (r < q_valid) {
+        __nv_bfloat16* orow = g.out + (long long)(k.q_row0 + t * kQT + r) * g.ldo + k.head * kD;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_O + c * 32, v);
-        tmem_ld_wait();
-        if (r < q_valid) {
+        for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t w4[4];
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2)
-              w4[k2] = pack_bf16(__uint_as_float(v[i * 8 + k2 * 2]) * inv, __uint_as_float(v[i * 8 + k2 * 2 + 1]) * inv);
-            *(reinterpret_cast<uint4*>(orow + c * 32) + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              w4[k2] = pack_bf16(__uint_as_float(o[cc][i * 8 + k2 * 2]) * inv, __uint_as_float(o[cc][i * 8 + k2 * 2 + 1]) * inv);
+            *(reinterpret_cast<uint4*>(orow + cc * 32) + i) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
           }
-        }
       }
     }
   }
@@ -389,9 +433,18 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  if (g.heads > 65535 || units > 65535) return fail(TTVDM_ERR_SHAPE, "attn: grid too large");
-  dim3 grid(g.q_tiles, g.heads, units);
-  attn_flash_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, g);
+  AttnArgs ga = g;
+  ga.units = units;
+  const long long works = (long long)g.q_tiles * g.heads * units;
+  if (works > 0x7fffffffLL) return fail(TTVDM_ERR_SHAPE, "attn: too many work items");
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(works < n_sm ? works : n_sm);  // persistent: one CTA per SM
+  attn_flash_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, ga);
   TTVDM_CHECK_LAUNCH("attn_flash_kernel");
   return 0;
 }
