@@ -854,9 +854,10 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     const bool legal = !g.b_resident && g.m_tiles >= 2 && g.block_n % 32 == 0 && (g.block_n / 2) % 8 == 0;
     if (legal) {
       if (e) pair = atoi(e) != 0;
-      // measured on B200 (tools/gpu_kernel_check.py --time): +5-10 % for K >= 640 with N >= 640, neutral or negative for
-      // the K = 320 / N = 320 level-0 shapes (epilogue / HBM bound)
-      else pair = (ktot_pre >= 640) && (p->N >= 640) && ((long long)g.m_tiles * g.n_tiles >= 2 * g_num_sms);
+      // measured on B200 (tools/gpu_kernel_check.py --time): +5-10 % for K >= 640 with N >= 640 and for the long-K
+      // 3x3 convolutions of any width (level-0 conv K = 2880, N = 320: 0.413 -> 0.381 ms; level-3 conv: 0.133 -> 0.125 ms),
+      // neutral or negative for the K = 320 level-0 linears and GEGLU (epilogue / HBM bound)
+      else pair = ((ktot_pre >= 640 && p->N >= 640) || ktot_pre >= 2048) && ((long long)g.m_tiles * g.n_tiles >= g_num_sms / 2);
     }
   }
   const int num_tiles = g.m_tiles * g.n_tiles;
