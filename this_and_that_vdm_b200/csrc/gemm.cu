@@ -269,7 +269,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int b_chunk_bytes = (g.block_n / kCtas) * kBlockK * 2;  // CTA pair: each CTA stages half of the W tile
   const int stage_bytes = g.b_resident ? kABytes : kABytes + b_chunk_bytes;
   const int cta_rank = kCtas == 2 ? (int)cluster_ctarank() : 0;
-  uint8_t* bres = tiles + g.stages * stage_bytes;  // b_resident only (never together with the TMA epilogue)
+  // b_resident only: the pinned W tile sits behind the operand ring and the TMA-epilogue staging buffers
+  uint8_t* bres = tiles + g.stages * stage_bytes + (g.tma_epi ? kEpiWarps * kEpiBufBytes : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -712,13 +713,13 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     if (force_direct) g.tma_epi = 0;
   }
   const int epi_bytes = g.tma_epi ? kEpiWarps * kEpiBufBytes : 0;
-  // B-resident schedule for short-K, many-M-tile GEMMs with the direct epilogue (GEGLU): re-streaming the W tile from
-  // L2 for every 128 rows makes them L2->SM bandwidth bound; pinning one N tile per CTA cuts the traffic per tile from
-  // (128 + BN) * K to 128 * K elements
+  // B-resident schedule for short-K, many-M-tile GEMMs (the K = 320 level-0 linears): re-streaming the W tile from L2 for
+  // every 128 rows makes them L2->SM bandwidth bound; pinning one N tile per CTA cuts the operand traffic per tile from
+  // (128 + BN) * K to 128 * K elements. Needs the W tile, the epilogue staging and >= 3 A stages in shared memory.
   const int b_res_bytes = g.taps * ((p->k1 + k2) / kBlockK) * g.block_n * kBlockK * 2;
   int stage_b = stage_bytes;
   g.b_resident = 0;
-  if (!g.tma_epi && p->mode == TTVDM_A_LINEAR && b_res_bytes <= 160 * 1024 && g.n_tiles <= g_num_sms / 4 &&
+  if (p->mode == TTVDM_A_LINEAR && b_res_bytes + epi_bytes + 3 * kABytes + 2048 <= kSmemBudget && g.n_tiles <= g_num_sms / 4 &&
       (p->M + kBlockM - 1) / kBlockM >= 8 * (g_num_sms / g.n_tiles)) {
     g.b_resident = 1;
     g.ctas_per_n = g_num_sms / g.n_tiles;
