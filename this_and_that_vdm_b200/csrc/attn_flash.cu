@@ -1,4 +1,4 @@
-// K5 / K6 / K8 — flash-style attention on tcgen05 for head_dim 64.
+// K5 — flash-style spatial self-attention on tcgen05 for head_dim 64.
 //
 //   S = Q K^T   : tcgen05.mma (SS) M=128 N=128 K=16 x 4, Q/K tiles staged by TMA (128B swizzle), S_t in TMEM
 //   softmax     : 128 threads per Q tile (one query row each) pull the whole S row into registers with four
@@ -29,10 +29,8 @@
 //   groups per row (shared or split accumulators), refilling S registers under the exponentials (software pipelining),
 //   a forced half-phase skew between the tiles, and moving a quarter of the exp2 to an FMA-pipe polynomial.
 // 192 KB smem (two Q buffers + 4-deep K/V ring), all 512 TMEM columns, one persistent CTA per SM (see the kernel).
-// The same kernel serves spatial self-attention (KV = the image's own tokens), spatial cross-attention (one KV
-// tile = the <=128 context tokens of the image's batch element) and temporal cross-attention, where the
-// reference's context-selection quirk (row (b,s) reads context (b*S+s) mod B,
-// svd/diffusion_arch/transformer_temporal.py:310-319) becomes a per-row mask over one KV tile per context.
+// Cross-attention against the 77-token CLIP context has its own kernel (attn_cross.cu): one small K/V tile per
+// (context, head) does not need this machinery.
 #include <cstdlib>
 
 #include "common.h"
@@ -52,17 +50,12 @@ constexpr int kAttnSmem = kTileBytes * (2 * kQTiles + 2 * kKV) + 512;
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
 
 
-enum { KV_SELF = 0, KV_CROSS_SPATIAL = 1, KV_CROSS_TEMPORAL = 2 };
-
 struct AttnArgs {
-  int kv_mode;
   int seq_q;      // query rows per unit (image)
-  int seq_kv;     // SELF: keys per unit; CROSS: L
+  int seq_kv;     // keys per unit (= seq_q: self-attention)
   int q_tiles;    // work items per (unit, head) = ceil(seq_q / 256)
   int heads;
-  int units;      // images (SELF) / (b, f) pairs (CROSS)
-  int F, S;       // rows ordered (b, f, s); unit = (b, f)
-  int n_ctx, batch_offset;
+  int units;      // images
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* out;
   int ldo;
@@ -119,8 +112,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // ---- persistent CTA: work item w = (q tile pair, head, unit), w = blockIdx.x, blockIdx.x + gridDim.x, ...
   // Barriers, TMEM and the pipeline state live across work items (all parities come from running counters), so the
   // next item's Q/K/V loads and its first Q K^T overlap the previous item's last P V and its output stores. This is
-  // what makes the cross-attention calls (ONE KV tile per item) and the low-resolution levels efficient: with one
-  // CTA per item they paid ~5 us of set-up and exposed latency per ~1 us of work.
+  // what keeps the low-resolution levels (few KV tiles per item) efficient: with one CTA per item they paid ~5 us of
+  // set-up and exposed latency per item.
   const int total_works = g.q_tiles * g.heads * g.units;
   struct Work {
     int q_row0, q_left, head, n_kv_tiles, kv_row_base;
@@ -133,16 +126,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int unit = hu / g.heads;
     k.q_row0 = unit * g.seq_q + qt * (kQT * kQTiles);  // global query row of Q tile 0, row 0
     k.q_left = g.seq_q - qt * (kQT * kQTiles);          // valid query rows of this item (> 0)
-    if (g.kv_mode == KV_SELF) {
-      k.n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
-      k.kv_row_base = unit * g.seq_kv;
-    } else if (g.kv_mode == KV_CROSS_SPATIAL) {
-      k.n_kv_tiles = 1;
-      k.kv_row_base = (g.batch_offset + unit / g.F) * g.seq_kv;
-    } else {
-      k.n_kv_tiles = g.n_ctx;
-      k.kv_row_base = 0;
-    }
+    k.n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
+    k.kv_row_base = unit * g.seq_kv;
     return k;
   };
 
@@ -196,7 +181,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int j = 0; j < k.n_kv_tiles; ++j, ++kt) {
           const int st = kt % kKV;
           const uint32_t ph = (kt / kKV) & 1;
-          const int kv_row = (g.kv_mode == KV_CROSS_TEMPORAL) ? j * g.seq_kv : k.kv_row_base + j * kKT;
+          const int kv_row = k.kv_row_base + j * kKT;
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_expect_tx(&k_full[st], kTileBytes);
           tma_load_2d(sK + st * kTileBytes, &tmK, &k_full[st], k.head * kD, kv_row);
@@ -258,8 +243,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           TR(0x20 + t);
           // P_t (128 x 128 bf16 pairs in TMEM) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
           const uint32_t sv = smem_u32(sV + st * kTileBytes);
-          const int kv_valid = (g.kv_mode == KV_SELF) ? min(kKT, g.seq_kv - j * kKT) : g.seq_kv;
-          const int nk = (kv_valid + 15) >> 4;  // only the 16-key steps that hold a valid key
+          const int nk = (min(kKT, g.seq_kv - j * kKT) + 15) >> 4;  // only the 16-key steps that hold a valid key
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             if (kk < nk)
@@ -291,20 +275,11 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int w = blockIdx.x; w < total_works; w += gridDim.x) {
       const Work k = decode(w);
       const int q_valid = min(kQT, k.q_left - t * kQT);  // <= 0: this tile carries no row of the item
-      int my_ctx = -1;
-      if (g.kv_mode == KV_CROSS_TEMPORAL) {
-        // global row -> (b, f, s); temporal batch row (b, s) reads context (b*S + s) mod n_ctx  [reference quirk]
-        const long long row = (long long)k.q_row0 + t * kQT + r;
-        const int s = (int)(row % g.S);
-        const int b = (int)(row / ((long long)g.F * g.S)) + g.batch_offset;
-        my_ctx = (int)(((long long)b * g.S + s) % g.n_ctx);
-      }
       float m_used = -INFINITY;  // (stale) row max the exponentials are taken against
       float l_run = 0.f;
       for (int j = 0; j < k.n_kv_tiles; ++j, ++c) {
-        const int kv_valid = (g.kv_mode == KV_SELF) ? min(kKT, g.seq_kv - j * kKT) : g.seq_kv;
-        const bool row_off = (g.kv_mode == KV_CROSS_TEMPORAL) && (my_ctx != j);
-        const bool masked = (kv_valid < kKT) || (g.kv_mode == KV_CROSS_TEMPORAL);  // CTA-uniform
+        const int kv_valid = min(kKT, g.seq_kv - j * kKT);
+        const bool masked = kv_valid < kKT;  // CTA-uniform: ragged last KV tile
         TR(1);
         mbar_wait(&s_full[t], c & 1);
         tc_fence_after();
@@ -322,7 +297,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (row_off || cc * 32 + i >= kv_valid) v[cc][i] = 0xff800000u;  // -inf
+              if (cc * 32 + i >= kv_valid) v[cc][i] = 0xff800000u;  // -inf
         }
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains of 3-input max
 #pragma unroll
@@ -359,7 +334,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t pk[2][32];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          if (masked && cc * 32 >= kv_valid) {  // CTA-uniform: a chunk without a valid key (cross-attention: keys 96..127)
+          if (masked && cc * 32 >= kv_valid) {  // CTA-uniform: a chunk without a valid key
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[cc >> 1][(cc & 1) * 16 + i] = 0u;
             continue;
@@ -468,15 +443,10 @@ extern "C" int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream_) {
   if (p->n_img <= 0 || p->heads <= 0 || p->seq <= 0) return fail(TTVDM_ERR_SHAPE, "attn_spatial: empty");
   if ((p->ldq | p->ldk | p->ldv | p->ldo) % 8 != 0) return fail(TTVDM_ERR_SHAPE, "attn_spatial: ld %% 8 != 0");
   AttnArgs g{};
-  g.kv_mode = KV_SELF;
   g.seq_q = p->seq;
   g.seq_kv = p->seq;
   g.q_tiles = (p->seq + kQT * kQTiles - 1) / (kQT * kQTiles);
   g.heads = p->heads;
-  g.F = 1;
-  g.S = p->seq;
-  g.n_ctx = 1;
-  g.batch_offset = 0;
   g.scale_log2 = p->scale * 1.4426950408889634f;
   g.out = static_cast<__nv_bfloat16*>(p->out);
   g.ldo = p->ldo;
@@ -485,33 +455,5 @@ extern "C" int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream_) {
 #endif
   const long long rows = (long long)p->n_img * p->seq;
   return launch_attn(p->q, p->ldq, rows, p->k, p->ldk, p->v, p->ldv, rows, g, p->n_img,
-                     static_cast<cudaStream_t>(stream_));
-}
-
-extern "C" int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream_) {
-  if (int rc = ensure_init()) return rc;
-  if (!p || !p->q || !p->kc || !p->vc || !p->out) return fail(TTVDM_ERR_SHAPE, "attn_cross: null");
-  if (p->L <= 0 || p->L > kKT) return fail(TTVDM_ERR_SHAPE, "attn_cross: L=%d (1..128)", p->L);
-  if (p->F <= 0 || p->S <= 0 || p->rows <= 0 || p->rows % (p->F * p->S) != 0)
-    return fail(TTVDM_ERR_SHAPE, "attn_cross: rows=%d not a multiple of F*S=%d", p->rows, p->F * p->S);
-  if ((p->ldq | p->ldo) % 8 != 0) return fail(TTVDM_ERR_SHAPE, "attn_cross: ld %% 8 != 0");
-  const int b_local = p->rows / (p->F * p->S);
-  if (p->n_ctx <= 0 || (!p->temporal && p->batch_offset + b_local > p->n_ctx))
-    return fail(TTVDM_ERR_SHAPE, "attn_cross: batch %d+%d exceeds n_ctx=%d", p->batch_offset, b_local, p->n_ctx);
-  AttnArgs g{};
-  g.kv_mode = p->temporal ? KV_CROSS_TEMPORAL : KV_CROSS_SPATIAL;
-  g.seq_q = p->S;
-  g.seq_kv = p->L;
-  g.q_tiles = (p->S + kQT * kQTiles - 1) / (kQT * kQTiles);
-  g.heads = p->heads;
-  g.F = p->F;
-  g.S = p->S;
-  g.n_ctx = p->n_ctx;
-  g.batch_offset = p->batch_offset;
-  g.scale_log2 = p->scale * 1.4426950408889634f;
-  g.out = static_cast<__nv_bfloat16*>(p->out);
-  g.ldo = p->ldo;
-  const int C = p->heads * kD;
-  return launch_attn(p->q, p->ldq, p->rows, p->kc, C, p->vc, C, (long long)p->n_ctx * p->L, g, b_local * p->F,
                      static_cast<cudaStream_t>(stream_));
 }

@@ -10,7 +10,7 @@ echo "gemm full rc=$?"
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attn_flash -c 2 \
     -o gpurun_out/prof_attn -f python bench.py --profile-only > gpurun_out/profile_attn.log 2>&1
 echo "attn full rc=$?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gn_ -c 2 \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:gn_|layernorm|attn_temporal" -c 28 \
     -o gpurun_out/prof_gn -f python bench.py --profile-only > gpurun_out/profile_gn.log 2>&1
-echo "gn full rc=$?"
+echo "gn / layernorm / attn_temporal full rc=$?"
 ls -la gpurun_out/
