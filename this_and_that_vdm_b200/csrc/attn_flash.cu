@@ -243,11 +243,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           TR(0x20 + t);
           // P_t (128 x 128 bf16 pairs in TMEM) * V_j (128 keys x 64, MN-major: 8-key groups 1024 B apart)
           const uint32_t sv = smem_u32(sV + st * kTileBytes);
-          const int nk = (min(kKT, g.seq_kv - j * kKT) + 15) >> 4;  // only the 16-key steps that hold a valid key
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
-            if (kk < nk)
-              tc_mma_ts(d_o, a_p + kk * 8, make_sdesc_sw128(sv + kk * 2048, 16, 1024), idesc_pv, (j | kk) != 0);
+            tc_mma_ts(d_o, a_p + kk * 8, make_sdesc_sw128(sv + kk * 2048, 16, 1024), idesc_pv, (j | kk) != 0);
           tc_commit(&o_done[t]);
           tc_commit(&v_empty[st]);  // one of kQTiles arrivals
           TR(0x28 + t);
@@ -333,12 +331,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float sum0 = 0.f, sum1 = 0.f;
         uint32_t pk[2][32];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          if (masked && cc * 32 >= kv_valid) {  // CTA-uniform: a chunk without a valid key
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[cc >> 1][(cc & 1) * 16 + i] = 0u;
-            continue;
-          }
+        for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float p0 = ex2(fmaf(__uint_as_float(v[cc][i]), c2, -ms));  // exp2(-inf) = 0 for masked keys
@@ -347,7 +340,6 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             sum1 += p1;
             pk[cc >> 1][(cc & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
           }
-        }
         l_run += sum0 + sum1;
         TR(5);
         if (j > 0) {
