@@ -102,7 +102,8 @@ typedef struct {
 int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K6/K8 — cross-attention against a short, precomputed context (L <= 128 keys).
+ * K6/K8 — cross-attention against a short, precomputed context (L <= 128 keys); warp-level mma.sync kernel with
+ * K/V of one (context, head) pinned in shared memory. q, kc, vc, out must be 16-byte aligned.
  * q: [rows, heads*64] (row stride ldq). kc/vc: [n_ctx, L, heads*64] bf16 — K/V of the constant context,
  * projected ONCE per video (reference recomputes them per frame and per pixel,
  * svd/unet_spatio_temporal_condition.py:452, svd/diffusion_arch/transformer_temporal.py:316-319).
@@ -125,7 +126,7 @@ typedef struct {
 int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K7 — temporal self-attention over the F (<= 32) frames of each (b, s, head); rows ordered (b, f, s),
+ * K7 — temporal self-attention over the F (<= 16) frames of each (b, s, head); rows ordered (b, f, s),
  * i.e. the kernel walks frames with stride S*ld instead of materialising the reference's
  * `(b f) s c -> (b s) f c` permute (diffusers TemporalBasicTransformerBlock.attn1).
  * ------------------------------------------------------------------------------------------------ */
