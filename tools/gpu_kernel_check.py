@@ -259,7 +259,15 @@ CASES = [
     ("attn_cross_temporal", lambda: case_attn_cross(temporal=True)),
     ("attn_cross_temporal_shard", lambda: case_attn_cross(B=1, temporal=True, batch_offset=1, S=97 - 1)),
     ("attn_cross_temporal_oddS", lambda: case_attn_cross(B=2, F=2, S=135, temporal=True)),
+    ("attn_cross_spatial_L128", lambda: case_attn_cross(B=2, F=2, S=50, heads=3, L=128)),
+    ("attn_cross_spatial_L17_tinyS", lambda: case_attn_cross(B=3, F=2, S=5, heads=2, L=17, n_ctx=3)),
+    ("attn_cross_temporal_3ctx", lambda: case_attn_cross(B=3, F=2, S=70, heads=2, L=33, temporal=True, n_ctx=3)),
+    ("attn_cross_temporal_3ctx_shard", lambda: case_attn_cross(B=1, F=3, S=49, heads=2, L=64, temporal=True, n_ctx=3, batch_offset=2)),
     ("attn_temporal", lambda: case_attn_temporal()),
+    ("attn_temporal_F16", lambda: case_attn_temporal(B=1, F=16, S=33, heads=2)),
+    ("attn_temporal_F3_ragged", lambda: case_attn_temporal(B=2, F=3, S=7, heads=3)),
+    ("layernorm_generic_C200", lambda: case_layernorm(rows=333, C=200)),
+    ("layernorm_320_add", lambda: case_layernorm(rows=14 * 9 * 2 + 0, C=320, add=True, S=9)),
     ("groupnorm_4d", lambda: case_groupnorm()),
     ("groupnorm_c64", lambda: case_groupnorm(n_inst=3, rows_per_inst=77, c1=64, silu=False)),
     ("groupnorm_concat", lambda: case_groupnorm(c1=1280, c2=640, silu=True)),
