@@ -17,14 +17,17 @@
 // MUFU-free phases (TMEM round trips, max, publishing P) can fall under the other tile's exponentials.
 // What bounds the kernel (measured with the clock64 event trace behind -DTTVDM_ATTN_TRACE, tools/attn_trace.py, and
 // tools/microbench/mma_rate.cu / mma_group.cu):
-//   * MUFU.EX2: 16/clk/SM = 1024 cycles per 128 x 128 tile against 512 cycles of tensor pipe (Q K^T 4 x 64, P V 8 x 32);
-//   * the ISSUING THREAD, not the tensor pipe, bounded round 1's kernel: (a) under `if (lane == 0)` ptxas wraps every
-//     tcgen05.mma in an ELECT / 4 x R2UR / branch sequence (~65 cycles per MMA, twice the cost of a 128x64x16 MMA) —
-//     under elect.sync the descriptors stay in uniform registers and MMAs issue back to back; (b) one thread is slow
-//     at everything else (an mbarrier wait is a ~130-cycle shared-memory round trip, scalar code runs at one
-//     instruction per 6-10 cycles next to two busy softmax warps), so one issuer serving both tiles spent ~800
-//     cycles per chain and forced the tiles into a fixed order; one issuer per tile with a fixed sequence of
-//     blocking waits removed that; (c) P through shared memory cost 64 KB of smem writes + reads per KV tile.
+//   * MUFU.EX2: 16/clk/SM = 1024 cycles per 128 x 128 tile;
+//   * the tensor pipe runs one accumulation chain at a time and every chain pays ~330 cycles of latency: 4 x N128
+//     (Q K^T) = 507 cycles, 8 x N64 (P V) = 652 — 2318 cycles per KV tile for both Q tiles, although the MMAs themselves
+//     are only 1024 cycles of work. The kernel needs ~2550 cycles per KV tile: within 10 % of the chain bound;
+//   * the ISSUING THREAD bounded round 1's kernel: (a) under `if (lane == 0)` ptxas wraps every tcgen05.mma in an
+//     ELECT / 4 x R2UR / branch sequence (30-60 cycles per MMA) — under elect.sync the descriptors stay in uniform
+//     registers and MMAs issue back to back; (b) one thread is slow at everything else (an mbarrier wait is a
+//     ~130-cycle shared-memory round trip, scalar code runs at one instruction per 6-10 cycles next to two busy softmax
+//     warps), so one issuer serving both tiles spent ~800 cycles per chain and forced the tiles into a fixed order;
+//     one issuer per tile with a fixed sequence of blocking waits removed that; (c) P through shared memory cost
+//     64 KB of smem writes + reads per KV tile.
 //   Tried and measured slower on the same box: a polling scheduler over both tiles, 256-key KV tiles with two key
 //   groups per row (shared or split accumulators), refilling S registers under the exponentials (software pipelining),
 //   a forced half-phase skew between the tiles, and moving a quarter of the exp2 to an FMA-pipe polynomial.

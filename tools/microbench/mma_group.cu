@@ -1,11 +1,15 @@
-// Microbenchmark: cost of a GROUP of n back-to-back tcgen05.mma (SS, M128 N128 K16, one accumulator chain) as a function
-// of n, with / without switching accumulator + operand buffers between groups, with / without a tcgen05.commit per group.
+// Microbenchmark: cost of a GROUP of n back-to-back tcgen05.mma (SS, M128 N=64/128/256 K16, one accumulator chain) as a
+// function of n, issued (a) under `if (threadIdx.x == 32)` and (b) under `if (elect_one())` (elect.sync).
+// With (a) ptxas cannot prove the descriptor operands warp-uniform and wraps every MMA in ELECT + R2UR + branch
+// instructions: the measured cost is ~65-85 cycles per MMA whatever N is (issue-bound) plus ~200 cycles per group;
+// with (b) descriptors live in uniform registers and the cost is the tensor pipe's (N/2 cycles per MMA at M = 128).
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../this_and_that_vdm_b200/csrc/ptx.cuh"
 using namespace ttvdm;
 constexpr int kTile = 16384;
 
+template <bool kElect>
 __global__ void __launch_bounds__(128, 1) grp(int n, int sw, int commit, int N, int groups, long long* out, int extra = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t done, bar[2];
@@ -19,7 +23,7 @@ __global__ void __launch_bounds__(128, 1) grp(int n, int sw, int commit, int N, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = slot;
-  if (threadIdx.x == 32) {
+  if (kElect ? (warp == 1 && elect_one()) : (threadIdx.x == 32)) {
     const uint32_t id = make_idesc_bf16(128, N, 0, 0);
     const uint64_t a0 = make_sdesc_sw128(smem_u32(smem), 16, 1024), b0 = make_sdesc_sw128(smem_u32(smem + 2 * kTile), 16, 1024);
     long long t0 = clock64();
@@ -43,30 +47,26 @@ __global__ void __launch_bounds__(128, 1) grp(int n, int sw, int commit, int N, 
   if (warp == 2) tmem_dealloc<512>(tm);
 }
 
+template <bool kElect>
+static void sweep(long long* d, const char* how) {
+  cudaFuncSetAttribute(grp<kElect>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTile + 1024);
+  const int groups = 256;
+  for (int N : {64, 128, 256}) {
+    printf("%-22s N=%3d (one chain per group, commit per group):", how, N);
+    for (int n : {1, 2, 4, 8, 16, 32}) {
+      grp<kElect><<<1, 128, 4 * kTile + 1024>>>(n, 0, 1, N, groups, d, 0); cudaDeviceSynchronize();
+      grp<kElect><<<1, 128, 4 * kTile + 1024>>>(n, 0, 1, N, groups, d, 0);
+      cudaError_t e = cudaDeviceSynchronize();
+      long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+      printf("  n=%d: %.0f/grp (%.0f/mma)%s", n, h[1] / double(groups), h[1] / double(groups) / n, e ? cudaGetErrorString(e) : "");
+    }
+    printf("\n");
+  }
+}
+
 int main() {
   long long* d; cudaMalloc(&d, 128); cudaMemset(d, 0, 128);
-  cudaFuncSetAttribute(grp, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTile + 1024);
-  const int groups = 256;
-  for (int N : {64, 128})
-    for (int sw = 0; sw < 2; ++sw)
-      for (int commit = 0; commit < 2; ++commit) {
-        printf("N=%3d switch=%d commit=%d :", N, sw, commit);
-        for (int n : {1, 2, 4, 8, 16, 32}) {
-          grp<<<1, 128, 4 * kTile + 1024>>>(n, sw, commit, N, groups, d); cudaDeviceSynchronize();
-          grp<<<1, 128, 4 * kTile + 1024>>>(n, sw, commit, N, groups, d);
-          cudaError_t e = cudaDeviceSynchronize();
-          long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-          printf("  n=%d: %.0f/grp (%.0f/mma)%s", n, h[1] / double(groups), h[1] / double(groups) / n, e ? cudaGetErrorString(e) : "");
-        }
-        printf("\n");
-      }
-  for (int extra = 0; extra < 8; ++extra) {
-    printf("N=128 n=4 commit=1 extra(fence=%d clock+stg=%d probe=%d):", extra & 1, extra >> 1 & 1, extra >> 2 & 1);
-    grp<<<1, 128, 4 * kTile + 1024>>>(4, 1, 1, 128, groups, d, extra); cudaDeviceSynchronize();
-    grp<<<1, 128, 4 * kTile + 1024>>>(4, 1, 1, 128, groups, d, extra);
-    cudaError_t e = cudaDeviceSynchronize();
-    long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("  %.0f/grp %s\n", h[1] / double(groups), e ? cudaGetErrorString(e) : "");
-  }
+  sweep<false>(d, "if (threadIdx.x == 32)");
+  sweep<true>(d, "if (elect_one())");
   return 0;
 }
