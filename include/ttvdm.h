@@ -213,6 +213,27 @@ typedef struct {
 } ttvdm_euler_params;
 int ttvdm_sampler_euler_step(const ttvdm_euler_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Gesture rasteriser ("next" row of the scope table): the [F, 3, H, W] fp32 this/that condition of
+ * data_loader/video_this_that_dataset.py:28-130 (get_thisthat_sam; duplicated in app.py:282-328) — per point a
+ * 21x21 coloured square on a 255 image of the ORIGINAL frame size, cv2.filter2D with the 99x99 Gaussian
+ * (sigma 10, BORDER_REFLECT_101), cv2.resize INTER_CUBIC to (W, H), optional np.fliplr, / 255; frames without a
+ * point are zeros; later points overwrite earlier ones on the same frame. Points in data.txt order (point 0 is
+ * drawn [0,0,255], the others [0,255,0]; BGR order is kept, as in the reference).
+ * scratch: device, >= n_points * (H + W) floats. out: device fp32 [F, 3, H, W], fully written.
+ * ------------------------------------------------------------------------------------------------ */
+#define TTVDM_GESTURE_MAX_POINTS 16
+typedef struct {
+  int n_points;
+  int frame_idx[TTVDM_GESTURE_MAX_POINTS], vertical[TTVDM_GESTURE_MAX_POINTS], horizontal[TTVDM_GESTURE_MAX_POINTS];
+  int org_h, org_w;  /* size of the original frame (im_0.jpg) the coordinates refer to */
+  int H, W, F;
+  int dilate, flip;
+  void* scratch;
+  void* out;
+} ttvdm_gesture_params;
+int ttvdm_gesture_raster(const ttvdm_gesture_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,11 +93,25 @@ class EulerParams(C.Structure):
     ]
 
 
+GESTURE_MAX_POINTS = 16
+
+
+class GestureParams(C.Structure):
+    _fields_ = [
+        ("n_points", c_int),
+        ("frame_idx", c_int * GESTURE_MAX_POINTS), ("vertical", c_int * GESTURE_MAX_POINTS),
+        ("horizontal", c_int * GESTURE_MAX_POINTS),
+        ("org_h", c_int), ("org_w", c_int), ("H", c_int), ("W", c_int), ("F", c_int),
+        ("dilate", c_int), ("flip", c_int),
+        ("scratch", c_void_p), ("out", c_void_p),
+    ]
+
+
 EXPORTS = [
     "ttvdm_init", "ttvdm_last_error", "ttvdm_abi_version", "ttvdm_launch_count",
     "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
     "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
-    "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step",
+    "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step", "ttvdm_gesture_raster",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -298,6 +312,26 @@ def sampler_prepare(latents, image_latents, cond, model_in, *, c_pad, B_local, b
     p.model_in, p.c_pad = _ptr(model_in), c_pad
     p.B_local, p.batch_offset, p.F, p.h, p.w, p.sigma = B_local, batch_offset, F, h, w, sigma
     call("ttvdm_sampler_prepare", p)
+
+
+def gesture_raster(points, out, scratch, *, org_h, org_w, dilate=True, flip=False) -> None:
+    """points: sequence of (frame_idx, vertical, horizontal) in data.txt order; out: fp32 [F, 3, H, W] on the device;
+    scratch: fp32 device buffer with >= len(points) * (H + W) elements."""
+    if out.dtype != torch.float32 or out.dim() != 4 or out.shape[1] != 3 or not out.is_contiguous():
+        raise TtvdmError("gesture_raster: out must be a contiguous fp32 [F, 3, H, W] tensor")
+    if len(points) > GESTURE_MAX_POINTS:
+        raise TtvdmError(f"gesture_raster: at most {GESTURE_MAX_POINTS} points")
+    F, _, H, W = out.shape
+    if scratch.dtype != torch.float32 or scratch.numel() < max(1, len(points)) * (H + W):
+        raise TtvdmError("gesture_raster: scratch must hold len(points) * (H + W) floats")
+    p = GestureParams()
+    p.n_points = len(points)
+    for i, (f, v, h) in enumerate(points):
+        p.frame_idx[i], p.vertical[i], p.horizontal[i] = int(f), int(v), int(h)
+    p.org_h, p.org_w, p.H, p.W, p.F = int(org_h), int(org_w), H, W, F
+    p.dilate, p.flip = int(bool(dilate)), int(bool(flip))
+    p.scratch, p.out = _ptr(scratch), _ptr(out)
+    call("ttvdm_gesture_raster", p)
 
 
 def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigma, sigma_next) -> None:
