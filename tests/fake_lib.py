@@ -1,0 +1,264 @@
+"""*** TEST INFRASTRUCTURE ONLY *** — a torch-CPU emulation of the C-ABI entry points of include/ttvdm.h.
+
+Purpose: the `-m "not gpu"` suite has to cover the HOST logic of the engines (weight packing, buffer reuse, leading
+dimensions, the kernel schedule, epilogue-fusion arguments) in a container without a GPU. The engines talk to the
+kernels only through the wrappers of this_and_that_vdm_b200/lib.py, so the tests swap those wrappers for the
+functions below, each of which does — in plain torch, on the same raw-pointer view of the buffers (data pointer +
+leading dimension, never the tensor's own shape) — exactly what the header documents for the kernel. Results are
+rounded to bf16 wherever the kernel stores bf16.
+
+This is NOT a fallback: it lives under tests/, nothing in the product imports it (tests/test_boundary.py greps for
+that), and the product still raises without libttvdm_sm100.so / an sm_100 device. The emulation itself is validated
+by running the GPU-proven UNet / GestureNet engine through it against the oracle (tests/test_host_logic.py).
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as Fn
+
+from this_and_that_vdm_b200 import lib
+
+BF16 = torch.bfloat16
+_launches = 0
+
+
+def _mat(t: torch.Tensor, rows: int, cols: int, ld: int) -> torch.Tensor:
+    """The [rows, cols] matrix with row stride ld that starts at t's data pointer (what the kernel sees)."""
+    return torch.as_strided(t, (rows, cols), (ld, 1), t.storage_offset())
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda2=0, n_img=0, H=0, W=0, bias=None,
+         rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None, ldr1=0, s1=1.0, res2=None, ldr2=0, s2=1.0,
+         geglu=False, ldo=None, out_fp32=False, act=0) -> None:
+    assert k1 % 64 == 0 and k2 % 64 == 0, "gemm: k1 / k2 must be multiples of 64"
+    assert a.dtype == BF16 and w.dtype == BF16
+    lda = k1 if lda is None else lda
+    taps = {lib.A_LINEAR: 1, lib.A_CONV3X3: 9, lib.A_TCONV3: 3}[mode]
+    ktot = taps * (k1 + k2)
+    wm = _mat(w, N, ktot, ktot).float()
+    if mode == lib.A_LINEAR:
+        A = _mat(a, M, k1, lda).float()
+        if a2 is not None:
+            A = torch.cat([A, _mat(a2, M, k2, lda2 if lda2 else k2).float()], 1)
+        acc = A @ wm.t()
+    elif mode == lib.A_CONV3X3:
+        assert n_img * H * W == M and a2 is None
+        x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1).permute(0, 3, 1, 2)
+        acc = Fn.conv2d(x, wm.view(N, 3, 3, k1).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(M, N)
+    else:
+        assert n_img * H * W == M and a2 is None  # n_img = B, H = F, W = S
+        x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1)
+        xp = Fn.pad(x, (0, 0, 0, 0, 1, 1))
+        acc = sum(xp[:, t:t + H] @ wm[:, t * k1:(t + 1) * k1].t() for t in range(3)).reshape(M, N)
+    if bias is not None:
+        acc = acc + bias.float()[:N]
+    if rowvec is not None:
+        assert rows_per_vec > 0
+        n_vec = (M + rows_per_vec - 1) // rows_per_vec
+        rv = _mat(rowvec, n_vec, N, ldrv if ldrv else N).float()
+        acc = acc + rv.repeat_interleave(rows_per_vec, 0)[:M]
+    if geglu:
+        assert res1 is None and res2 is None and not out_fp32
+        val = s0 * acc[:, 0::2] * Fn.gelu(acc[:, 1::2])
+        n_out = N // 2
+    else:
+        val = s0 * acc
+        n_out = N
+        r1 = _mat(res1, M, N, ldr1 if ldr1 else N).float().clone() if res1 is not None else None
+        r2 = _mat(res2, M, N, ldr2 if ldr2 else N).float().clone() if res2 is not None else None
+        if r1 is not None:
+            val = val + s1 * r1
+        if r2 is not None:
+            val = val + s2 * r2
+        if act == 1:
+            val = Fn.silu(val)
+    ldo = ldo if ldo is not None else n_out
+    assert out.dtype == (torch.float32 if out_fp32 else BF16)
+    _mat(out, M, n_out, ldo).copy_(val.to(out.dtype))
+    _count()
+
+
+def _heads(t, rows, heads, ld, d=64):
+    return _mat(t, rows, heads * d, ld).float().view(rows, heads, d)
+
+
+def attn_spatial(q, k, v, out, *, ldq, ldk, ldv, ldo, n_img, heads, seq, scale) -> None:
+    rows = n_img * seq
+    qq, kk, vv = (_heads(t, rows, heads, ld).view(n_img, seq, heads, 64).permute(0, 2, 1, 3)
+                  for t, ld in ((q, ldq), (k, ldk), (v, ldv)))
+    p = torch.softmax(qq @ kk.transpose(-1, -2) * scale, -1)
+    o = (p @ vv).permute(0, 2, 1, 3).reshape(rows, heads * 64)
+    _mat(out, rows, heads * 64, ldo).copy_(o.to(BF16))
+    _count()
+
+
+def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale) -> None:
+    C = heads * 64
+    qq = _heads(q, rows, heads, ldq)
+    kk = _mat(kc, n_ctx * L, C, C).float().view(n_ctx, L, heads, 64)
+    vv = _mat(vc, n_ctx * L, C, C).float().view(n_ctx, L, heads, 64)
+    r = torch.arange(rows)
+    b = r // (F * S) + batch_offset
+    ctx = ((b * S + r % S) % n_ctx) if temporal else b
+    kr, vr = kk[ctx], vv[ctx]  # [rows, L, heads, 64]
+    s = torch.einsum("rhd,rlhd->rhl", qq, kr) * scale
+    o = torch.einsum("rhl,rlhd->rhd", torch.softmax(s, -1), vr).reshape(rows, C)
+    _mat(out, rows, C, ldo).copy_(o.to(BF16))
+    _count()
+
+
+def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) -> None:
+    rows = B * F * S
+    qq, kk, vv = (_heads(t, rows, heads, ld).view(B, F, S, heads, 64).permute(0, 2, 3, 1, 4)
+                  for t, ld in ((q, ldq), (k, ldk), (v, ldv)))  # [B, S, heads, F, 64]
+    p = torch.softmax(qq @ kk.transpose(-1, -2) * scale, -1)
+    o = (p @ vv).permute(0, 3, 1, 2, 4).reshape(rows, heads * 64)
+    _mat(out, rows, heads * 64, ldo).copy_(o.to(BF16))
+    _count()
+
+
+def groupnorm(x1, out, stats, gamma, beta, *, c1, rows, rows_per_inst, eps, silu, x2=None, c2=0, ld1=None, ld2=None,
+              ldo=None) -> None:
+    assert (c1 + c2) % 32 == 0 and c1 % 8 == 0 and c2 % 8 == 0 and rows % rows_per_inst == 0
+    assert stats.dtype == torch.float64 and stats.numel() >= (rows // rows_per_inst) * 64
+    x = _mat(x1, rows, c1, c1 if ld1 is None else ld1).float()
+    if x2 is not None:
+        x = torch.cat([x, _mat(x2, rows, c2, c2 if ld2 is None else ld2).float()], 1)
+    C = c1 + c2
+    n_inst = rows // rows_per_inst
+    xi = x.view(n_inst, rows_per_inst, C).permute(0, 2, 1)  # [inst, C, rows] == N, C, *
+    y = Fn.group_norm(xi, 32, gamma.float(), beta.float(), eps).permute(0, 2, 1).reshape(rows, C)
+    if silu:
+        y = Fn.silu(y)
+    _mat(out, rows, C, C if ldo is None else ldo).copy_(y.to(BF16))
+    _count(3)  # memset + stats + apply
+
+
+def layernorm(x, out, gamma, beta, *, rows, C, eps=1e-5, addvec=None, F=0, S=0, sum_out=None, ldx=None, ldo=None,
+              ldsum=None) -> None:
+    xx = _mat(x, rows, C, C if ldx is None else ldx).float()
+    if addvec is not None:
+        idx = (torch.arange(rows) // S) % F
+        xx = xx + _mat(addvec, F, C, C).float()[idx]
+    if sum_out is not None:
+        _mat(sum_out, rows, C, C if ldsum is None else ldsum).copy_(xx.to(BF16))
+    y = Fn.layer_norm(xx, (C,), gamma.float(), beta.float(), eps)
+    _mat(out, rows, C, C if ldo is None else ldo).copy_(y.to(BF16))
+    _count()
+
+
+def im2col_s2(x, out, *, n_img, H, W, C) -> None:
+    xi = _mat(x, n_img * H * W, C, C).float().view(n_img, H, W, C).permute(0, 3, 1, 2)
+    cols = Fn.unfold(xi, 3, padding=1, stride=2)  # [n, C*9, Ho*Wo], channel-major then tap
+    Ho, Wo = H // 2, W // 2
+    cols = cols.view(n_img, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(n_img * Ho * Wo, 9 * C)
+    _mat(out, n_img * Ho * Wo, 9 * C, 9 * C).copy_(cols.to(BF16))
+    _count()
+
+
+def upsample2x(x, out, *, n_img, H, W, C) -> None:
+    xi = _mat(x, n_img * H * W, C, C).view(n_img, H, W, C)
+    up = xi.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(n_img * 4 * H * W, C)
+    _mat(out, n_img * 4 * H * W, C, C).copy_(up)
+    _count()
+
+
+def sinusoid(t, out, *, n, dim) -> None:
+    half = dim // 2
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    arg = t.float().reshape(-1)[:n, None] * freq[None]
+    _mat(out, n, dim, dim).copy_(torch.cat([torch.cos(arg), torch.sin(arg)], 1).to(BF16))
+    _count()
+
+
+def axpy(a, b, out, scale, n) -> None:
+    val = a.reshape(-1)[:n].float() + scale * b.reshape(-1)[:n].float()
+    out.view(-1)[:n].copy_(val.to(out.dtype))
+    _count()
+
+
+def sampler_prepare(latents, image_latents, cond, model_in, *, c_pad, B_local, batch_offset, F, h, w, sigma) -> None:
+    x = torch.zeros(B_local, F, h, w, c_pad)
+    lat = (latents.float() / math.sqrt(sigma * sigma + 1.0)).permute(0, 2, 3, 1)  # [F, h, w, 4]
+    for b in range(B_local):
+        x[b, ..., 0:4] = lat
+        x[b, ..., 4:8] = image_latents[batch_offset + b].float().permute(1, 2, 0)[None]
+        if cond is not None:
+            x[b, ..., 8:12] = cond.float().permute(0, 2, 3, 1)
+    _mat(model_in, B_local * F * h * w, c_pad, c_pad).copy_(x.view(-1, c_pad).to(BF16))
+    _count()
+
+
+def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigma, sigma_next) -> None:
+    n = F * h * w
+    eu = _mat(eps_u, n, 4, ld_eps).float().view(F, h, w, 4).permute(0, 3, 1, 2)
+    ec = _mat(eps_c, n, 4, ld_eps).float().view(F, h, w, 4).permute(0, 3, 1, 2)
+    eps = eu + guidance.float().view(F, 1, 1, 1) * (ec - eu)
+    x = latents.float()
+    x0 = eps * (-sigma / math.sqrt(sigma * sigma + 1.0)) + x / (sigma * sigma + 1.0)
+    latents.copy_(x + (x - x0) / sigma * (sigma_next - sigma))
+    _count()
+
+
+# ---- VAE entry points (include/ttvdm.h "VAE" section)
+def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out) -> None:
+    p = torch.softmax(_mat(x, rows, cols, ldx).float(), -1)
+    o = torch.zeros(rows, cols_out)
+    o[:, :cols] = p
+    _mat(out, rows, cols_out, ldo).copy_(o.to(BF16))
+    _count()
+
+
+def im2col_s2_pad01(x, out, *, n_img, H, W, C) -> None:
+    """Downsample2D of the VAE encoder: F.pad(x, (0, 1, 0, 1)) then Conv2d(3, stride 2, padding 0)."""
+    xi = _mat(x, n_img * H * W, C, C).float().view(n_img, H, W, C).permute(0, 3, 1, 2)
+    cols = Fn.unfold(Fn.pad(xi, (0, 1, 0, 1)), 3, padding=0, stride=2)
+    Ho, Wo = H // 2, W // 2
+    cols = cols.view(n_img, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(n_img * Ho * Wo, 9 * C)
+    _mat(out, n_img * Ho * Wo, 9 * C, 9 * C).copy_(cols.to(BF16))
+    _count()
+
+
+def vae_time_conv_out(x, w, bias, out, *, B, F, H, W, ldx) -> None:
+    """x fp32 [(b, f, s), ldx] (3 real channels) -> out fp32 NCHW [B*F, 3, H, W]; Conv3d(3, 3, (3,1,1), pad (1,0,0))."""
+    S = H * W
+    xi = _mat(x, B * F * S, 3, ldx).float().view(B, F, S, 3).permute(0, 3, 1, 2)[..., None]  # [B, 3, F, S, 1]
+    y = Fn.conv3d(xi, w.float().view(3, 3, 3, 1, 1), bias.float(), padding=(1, 0, 0))  # [B, 3, F, S, 1]
+    out.view(B, F, 3, S).copy_(y[..., 0].permute(0, 2, 1, 3))
+    _count()
+
+
+def launch_count() -> int:
+    return _launches
+
+
+_PATCHED = ["gemm", "attn_spatial", "attn_cross", "attn_temporal", "groupnorm", "layernorm", "im2col_s2", "upsample2x",
+            "sinusoid", "axpy", "sampler_prepare", "sampler_euler_step", "softmax_rows", "im2col_s2_pad01",
+            "vae_time_conv_out", "launch_count"]
+
+
+@contextlib.contextmanager
+def installed():
+    """Swap the ctypes wrappers of this_and_that_vdm_b200.lib for the emulation (and make init() a no-op)."""
+    saved = {n: getattr(lib, n, None) for n in _PATCHED + ["init"]}
+    g = globals()
+    try:
+        for n in _PATCHED:
+            setattr(lib, n, g[n])
+        lib.init = lambda device=None: None
+        yield
+    finally:
+        for n, f in saved.items():
+            if f is None:
+                if hasattr(lib, n):
+                    delattr(lib, n)
+            else:
+                setattr(lib, n, f)

@@ -56,6 +56,7 @@ def test_no_cpu_fallback_and_no_oracle_import_in_product():
     for path in list((ROOT / "svd").rglob("*.py")) + list((ROOT / "this_and_that_vdm_b200").rglob("*.py")):
         txt = path.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, path
+        assert "fake_lib" not in txt and "from tests" not in txt and "import tests" not in txt, path
     if not torch.cuda.is_available():
         from this_and_that_vdm_b200 import lib
         with pytest.raises(lib.TtvdmError):
