@@ -234,6 +234,30 @@ typedef struct {
 } ttvdm_gesture_params;
 int ttvdm_gesture_raster(const ttvdm_gesture_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * VAE either side of the loop ("next" row of the scope table): diffusers AutoencoderKLTemporalDecoder as the reference
+ * calls it — vae.encode(image).latent_dist.mode() (svd/pipeline_stable_video_diffusion_controlnet.py:199, :652) and
+ * vae.decode(latents[i:i+chunk], num_frames=...) (:257-283). Its convolutions, GroupNorms, linears and the 3-tap
+ * temporal convolutions run on ttvdm_gemm / ttvdm_groupnorm / ttvdm_upsample2x above; the three entry points below
+ * are what only the VAE needs.
+ *
+ *  softmax_rows     : the mid-block Attention (ONE head of 512 dims over all H*W/64 tokens of a frame) is
+ *                     scores = ttvdm_gemm(Q, K) (fp32, scaled), P = softmax_rows(scores), out = ttvdm_gemm(P, V^T).
+ *                     x fp32 [rows, cols] (row stride ldx) -> out bf16 [rows, cols_out] (row stride ldo);
+ *                     columns [cols, cols_out) are written as 0 (K padding of the following GEMM).
+ *  im2col_s2_pad01  : Downsample2D(padding=0) of the encoder = F.pad(x, (0,1,0,1)) + Conv2d(C, C, 3, stride 2):
+ *                     gathers [n, H/2, W/2, 9*C] patches (tap-major, then channel) for a LINEAR GEMM.
+ *  vae_time_conv_out: TemporalDecoder.time_conv_out = Conv3d(3, 3, (3,1,1), padding (1,0,0)) over the frames of each
+ *                     video, fused with the channels-last -> NCHW conversion of the decoded frames.
+ *                     x: device fp32 [(b, f, s), ldx] (3 real channels per row); w / bias: HOST pointers to the 27
+ *                     weights [co][ci][t] and 3 biases (they travel in the kernel's parameter space);
+ *                     out: device fp32 [B*F, 3, S].
+ * ------------------------------------------------------------------------------------------------ */
+int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, int rows, int cols, int cols_out, void* stream);
+int ttvdm_im2col_s2_pad01(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
+int ttvdm_vae_time_conv_out(const float* x, int ldx, const float* w, const float* bias, float* out, int B, int F, int S,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,3 +64,35 @@ def make_inputs(B: int, F: int, h: int, w: int, L: int = 78, seed: int = 0):
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+# ---- VAE (AutoencoderKLTemporalDecoder) builders
+TINY_VAE = dict(block_out_channels=(64, 128, 128, 128), layers_per_block=1,
+                down_block_types=("DownEncoderBlock2D",) * 4)
+SVD_VAE = dict(block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+               down_block_types=("DownEncoderBlock2D",) * 4)
+
+
+def build_vae(kind: dict, seed: int = 4321):
+    from svd.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    torch.manual_seed(seed)
+    vae = AutoencoderKLTemporalDecoder(**kind).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, p in vae.named_parameters():
+            if name.endswith("mix_factor"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            elif "norm" in name:
+                if name.endswith("weight"):
+                    p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+                else:
+                    p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    return vae
+
+
+def vae_inputs(n_frames: int, lh: int, lw: int, n_images: int = 2, seed: int = 5):
+    """Latents [n_frames, 4, lh, lw] (unit scale, i.e. already / scaling_factor) and images [n_images, 3, 8lh, 8lw]."""
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(n_frames, 4, lh, lw, generator=g)
+    x = torch.rand(n_images, 3, 8 * lh, 8 * lw, generator=g) * 2.0 - 1.0
+    return z, x

@@ -1,0 +1,99 @@
+"""Host logic of this_and_that_vdm_b200/vae_engine.py on CPU (`-m "not gpu"`): packing (quant_conv fold, conv_out
+padding, AlphaBlender fold), the per-frame attention schedule with its padded P / V^T buffers, chunked per-image
+launches and the drop-in module surface — run through tests/fake_lib.py (torch emulation of the C ABI, validated by
+tests/test_host_logic.py on the GPU-proven UNet engine) against oracle/vae_oracle.py. The same engine code runs on
+the B200 against the real kernels in tests/test_vae_gpu.py. Tolerance: rel-L2 < 3e-2 vs the fp32 oracle (bf16 storage)."""
+import pytest
+import torch
+
+from oracle import vae_oracle as VO
+from tests import fake_lib
+from tests.common import TINY_VAE, build_vae, rel_l2, state, vae_inputs
+from this_and_that_vdm_b200 import vae_engine
+from this_and_that_vdm_b200.vae_engine import VaeEngine
+
+CAP = 3e-2
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    vae = build_vae(TINY_VAE)
+    with fake_lib.installed():
+        eng = VaeEngine(vae)
+    return vae, eng, state(vae)
+
+
+@pytest.mark.parametrize("n_videos,frames,lh,lw", [(1, 4, 8, 12), (2, 3, 4, 6), (1, 1, 5, 7)])
+def test_decode_schedule_vs_oracle(tiny, n_videos, frames, lh, lw):
+    vae, eng, sd = tiny
+    z, _ = vae_inputs(n_videos * frames, lh, lw)
+    with torch.no_grad(), fake_lib.installed():
+        out = eng.decode(z, frames)
+        ref = VO.decode(sd, z, frames)
+    assert out.shape == ref.shape == (n_videos * frames, 3, 8 * lh, 8 * lw)
+    assert rel_l2(out, ref) < CAP
+
+
+@pytest.mark.parametrize("n,lh,lw", [(2, 8, 12), (5, 3, 5)])
+def test_encode_schedule_vs_oracle(tiny, n, lh, lw):
+    vae, eng, sd = tiny
+    _, x = vae_inputs(1, lh, lw, n_images=n)
+    with torch.no_grad(), fake_lib.installed():
+        mom = eng.encode(x, max_images_per_pass=2)
+        ref = VO.encode(sd, x)
+    assert mom.shape == (n, 8, lh, lw)
+    assert rel_l2(mom[:, :4], ref) < CAP
+
+
+def test_chunked_launches_give_the_same_result(tiny, monkeypatch):
+    """Per-image ops are split so that no launch sees more than _MAX_ELEMS elements; force many groups."""
+    vae, eng, sd = tiny
+    z, _ = vae_inputs(4, 4, 6)
+    with torch.no_grad(), fake_lib.installed():
+        whole = eng.decode(z, 4)
+        monkeypatch.setattr(vae_engine, "_MAX_ELEMS", 4 * 6 * 64 * 3)
+        split = eng.decode(z, 4)
+        ref = VO.decode(sd, z, 4)
+    # same arithmetic per image; torch's CPU kernels block differently per batch size, so bf16 roundings flip and the
+    # two runs differ by bf16 noise — both must sit within the bar of the oracle
+    assert rel_l2(split, ref) < CAP and rel_l2(whole, ref) < CAP and rel_l2(split, whole) < CAP
+
+
+def test_module_surface_matches_diffusers_calls(tiny, monkeypatch):
+    """encode(x).latent_dist.mode(), decode(z, num_frames=n).sample, forward(num_frames=) as the pipelines call them
+    (svd/pipeline_stable_video_diffusion_controlnet.py:199, :257-283); CPU modules must refuse to run."""
+    import inspect
+    from svd.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    vae, eng, sd = tiny
+    assert "num_frames" in inspect.signature(vae.forward).parameters
+    assert vae.config.scaling_factor == 0.18215 and len(vae.config.block_out_channels) == 4
+    z, x = vae_inputs(2, 4, 6)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vae.encode(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vae.decode(z, num_frames=2)
+    with pytest.raises(ValueError, match="same number"):
+        AutoencoderKLTemporalDecoder(down_block_types=("DownEncoderBlock2D",) * 2, block_out_channels=(64,))
+    monkeypatch.setattr(type(vae), "_get_engine", lambda self: eng)
+    with torch.no_grad(), fake_lib.installed():
+        lat = vae.encode(x).latent_dist.mode()
+        dec = vae.decode(z, num_frames=2).sample
+        with pytest.raises(ValueError, match="multiple"):
+            vae.decode(z[:1].repeat(3, 1, 1, 1), num_frames=2)
+        ref_lat, ref_dec = VO.encode(sd, x), VO.decode(sd, z, 2)
+    assert rel_l2(lat, ref_lat) < CAP and rel_l2(dec, ref_dec) < CAP
+
+
+def test_pipeline_decode_latents_through_the_engine(tiny, monkeypatch):
+    """decode_latents of the drop-in pipelines: /scaling_factor, chunks of decode_chunk_size frames, [B, C, F, H, W]."""
+    from svd.pipeline_common import SVDPipelineBase
+    vae, eng, sd = tiny
+    monkeypatch.setattr(type(vae), "_get_engine", lambda self: eng)
+    pipe = SVDPipelineBase(vae=vae, unet=None)
+    g = torch.Generator().manual_seed(2)
+    lat = torch.randn(1, 6, 4, 4, 6, generator=g) * 0.18215
+    with torch.no_grad(), fake_lib.installed():
+        frames = pipe.decode_latents(lat, 6, decode_chunk_size=4)
+        ref = VO.decode_latents(sd, lat, 6, decode_chunk_size=4)
+    assert frames.shape == (1, 3, 6, 32, 48) and frames.dtype == torch.float32
+    assert rel_l2(frames, ref) < CAP

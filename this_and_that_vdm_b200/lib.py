@@ -112,6 +112,7 @@ EXPORTS = [
     "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
     "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
     "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step", "ttvdm_gesture_raster",
+    "ttvdm_softmax_rows", "ttvdm_im2col_s2_pad01", "ttvdm_vae_time_conv_out",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -339,3 +340,27 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
     p.latents, p.eps_u, p.eps_c, p.ld_eps = _ptr(latents), _ptr(eps_u), _ptr(eps_c), ld_eps
     p.guidance, p.F, p.h, p.w, p.sigma, p.sigma_next = _ptr(guidance), F, h, w, sigma, sigma_next
     call("ttvdm_sampler_euler_step", p)
+
+
+# ---- VAE-only entry points (include/ttvdm.h, "VAE either side of the loop")
+def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out) -> None:
+    """x fp32 [rows, cols] (ldx) -> out bf16 [rows, cols_out] (ldo); columns >= cols are written as zeros."""
+    if x.dtype != torch.float32 or out.dtype != torch.bfloat16:
+        raise TtvdmError("softmax_rows: x must be fp32 and out bf16")
+    call_raw("ttvdm_softmax_rows", c_void_p(_ptr(x)), ldx, c_void_p(_ptr(out)), ldo, rows, cols, cols_out)
+
+
+def im2col_s2_pad01(x, out, *, n_img, H, W, C) -> None:
+    call_raw("ttvdm_im2col_s2_pad01", c_void_p(_ptr(x)), c_void_p(_ptr(out)), n_img, H, W, C)
+
+
+def vae_time_conv_out(x, w, bias, out, *, B, F, H, W, ldx) -> None:
+    """x: device fp32 [(b, f, s), ldx]; w: HOST fp32 [3, 3, 3] (co, ci, t); bias: HOST fp32 [3];
+    out: device fp32 [B*F, 3, H, W]."""
+    if w.is_cuda or bias.is_cuda or w.dtype != torch.float32 or bias.dtype != torch.float32 or w.numel() != 27:
+        raise TtvdmError("vae_time_conv_out: w / bias must be host fp32 tensors with 27 / 3 elements")
+    if x.dtype != torch.float32 or out.dtype != torch.float32 or not out.is_contiguous():
+        raise TtvdmError("vae_time_conv_out: x / out must be fp32 (out contiguous)")
+    w, bias = w.contiguous(), bias.contiguous()
+    call_raw("ttvdm_vae_time_conv_out", c_void_p(_ptr(x)), ldx, c_void_p(w.data_ptr()), c_void_p(bias.data_ptr()),
+             c_void_p(_ptr(out)), B, F, H * W)
