@@ -244,7 +244,8 @@ int ttvdm_gesture_raster(const ttvdm_gesture_params* p, void* stream);
  *  softmax_rows     : the mid-block Attention (ONE head of 512 dims over all H*W/64 tokens of a frame) is
  *                     scores = ttvdm_gemm(Q, K) (fp32, scaled), P = softmax_rows(scores), out = ttvdm_gemm(P, V^T).
  *                     x fp32 [rows, cols] (row stride ldx) -> out bf16 [rows, cols_out] (row stride ldo);
- *                     columns [cols, cols_out) are written as 0 (K padding of the following GEMM).
+ *                     columns [cols, cols_out) are written as 0 (K padding of the following GEMM). causal = 1 (CLIP
+ *                     text tower): row r only attends to columns 0..r, the rest are written as 0.
  *  im2col_s2_pad01  : Downsample2D(padding=0) of the encoder = F.pad(x, (0,1,0,1)) + Conv2d(C, C, 3, stride 2):
  *                     gathers [n, H/2, W/2, 9*C] patches (tap-major, then channel) for a LINEAR GEMM.
  *  vae_time_conv_out: TemporalDecoder.time_conv_out = Conv3d(3, 3, (3,1,1), padding (1,0,0)) over the frames of each
@@ -253,10 +254,25 @@ int ttvdm_gesture_raster(const ttvdm_gesture_params* p, void* stream);
  *                     weights [co][ci][t] and 3 biases (they travel in the kernel's parameter space);
  *                     out: device fp32 [B*F, 3, S].
  * ------------------------------------------------------------------------------------------------ */
-int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, int rows, int cols, int cols_out, void* stream);
+int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, int rows, int cols, int cols_out, int causal,
+                       void* stream);
 int ttvdm_im2col_s2_pad01(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
 int ttvdm_vae_time_conv_out(const float* x, int ldx, const float* w, const float* bias, float* out, int B, int F, int S,
                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Conditioning builder ("next" row #2): encode_clip (svd/pipeline_stable_video_diffusion_controlnet.py:130-188) — CLIP
+ * image tower (transformers CLIPVisionModelWithProjection, `self.image_encoder(image).image_embeds`, :155), CLIP text
+ * tower (CLIPTextModel, `text_encoder(prompt)[0]`, :166), concat, a fresh nn.LayerNorm((78, 1024)) (:172-173) and the
+ * CFG zero stack. Linears / attention GEMMs run on ttvdm_gemm, LayerNorms on ttvdm_layernorm, softmax on
+ * ttvdm_softmax_rows (causal for the text tower); the two entry points below are what only this row needs.
+ *  act_inplace    : the towers' MLP activation on a bf16 buffer; kind 2 = GELU (erf form, `hidden_act: "gelu"` of the
+ *                   ViT-H / SD-2.1 text checkpoints), kind 3 = quick GELU x*sigmoid(1.702x) (OpenAI CLIP checkpoints).
+ *  layernorm_flat : out[r, :] = (x[r, :] - mean_r) / sqrt(var_r + eps) over ALL n elements of row r (normalized_shape
+ *                   = (78, 1024), no affine: the reference's LayerNorm is freshly constructed). fp32 in / out.
+ * ------------------------------------------------------------------------------------------------ */
+int ttvdm_act_inplace(void* x, size_t n, int kind, void* stream);
+int ttvdm_layernorm_flat(const float* x, float* out, int rows, size_t n, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,10 @@ class AutoencoderKLTemporalDecoder(ModelBase):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
     @torch.no_grad()
     def encode(self, x: torch.FloatTensor, return_dict: bool = True):
         moments = self._get_engine().encode(x)

@@ -209,8 +209,11 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
 
 
 # ---- VAE entry points (include/ttvdm.h "VAE" section)
-def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out) -> None:
-    p = torch.softmax(_mat(x, rows, cols, ldx).float(), -1)
+def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out, causal=False) -> None:
+    sc = _mat(x, rows, cols, ldx).float()
+    if causal:
+        sc = sc.masked_fill(torch.arange(cols)[None, :] > torch.arange(rows)[:, None], float("-inf"))
+    p = torch.softmax(sc, -1)
     o = torch.zeros(rows, cols_out)
     o[:, :cols] = p
     _mat(out, rows, cols_out, ldo).copy_(o.to(BF16))
@@ -236,13 +239,24 @@ def vae_time_conv_out(x, w, bias, out, *, B, F, H, W, ldx) -> None:
     _count()
 
 
+def act_inplace(x, kind) -> None:
+    v = x.float()
+    x.copy_((Fn.gelu(v) if kind == 2 else v * torch.sigmoid(1.702 * v)).to(BF16))
+    _count()
+
+
+def layernorm_flat(x, out, *, rows, n, eps=1e-5) -> None:
+    out.view(rows, n).copy_(Fn.layer_norm(x.view(rows, n).float(), (n,), None, None, eps))
+    _count()
+
+
 def launch_count() -> int:
     return _launches
 
 
 _PATCHED = ["gemm", "attn_spatial", "attn_cross", "attn_temporal", "groupnorm", "layernorm", "im2col_s2", "upsample2x",
             "sinusoid", "axpy", "sampler_prepare", "sampler_euler_step", "softmax_rows", "im2col_s2_pad01",
-            "vae_time_conv_out", "launch_count"]
+            "vae_time_conv_out", "act_inplace", "layernorm_flat", "launch_count"]
 
 
 @contextlib.contextmanager

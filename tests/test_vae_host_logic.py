@@ -97,3 +97,21 @@ def test_pipeline_decode_latents_through_the_engine(tiny, monkeypatch):
         ref = VO.decode_latents(sd, lat, 6, decode_chunk_size=4)
     assert frames.shape == (1, 3, 6, 32, 48) and frames.dtype == torch.float32
     assert rel_l2(frames, ref) < CAP
+
+
+def test_encode_dedupes_identical_images(tiny):
+    """12 of the reference's 14 gesture frames are all-zero: identical images are encoded once and scattered back."""
+    vae, eng, sd = tiny
+    _, x = vae_inputs(1, 4, 6, n_images=2)
+    zero = torch.zeros_like(x[:1])
+    batch = torch.cat([zero, x[:1], zero, zero, x[1:], zero])
+    with torch.no_grad(), fake_lib.installed():
+        n0 = fake_lib.launch_count()
+        a = eng.encode(batch)
+        n_dedup = fake_lib.launch_count() - n0
+        b = eng.encode(batch, dedupe=False)
+        n_all = fake_lib.launch_count() - n0 - n_dedup
+    assert a.shape == b.shape == (6, 8, 4, 6)
+    assert torch.equal(a[0], a[2]) and torch.equal(a[0], a[5]) and not torch.equal(a[0], a[1])
+    assert rel_l2(a, b) < CAP and rel_l2(a[:, :4], VO.encode(sd, batch)) < CAP
+    assert n_dedup * 2 == n_all  # 3 distinct images instead of 6

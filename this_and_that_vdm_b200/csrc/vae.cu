@@ -31,9 +31,11 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) 
 // re-read (rows longer than the shared-memory budget).
 template <bool CACHED>
 __global__ void __launch_bounds__(kSoftmaxThreads)
-softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo, int cols,
-                    int cols_out) {
+softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo, int cols_all,
+                    int cols_out, int causal) {
   extern __shared__ float row[];
+  // causal (CLIP text tower): row r attends to keys 0..r; the masked probabilities are written as zeros
+  const int cols = causal ? min(cols_all, (int)blockIdx.x + 1) : cols_all;
   __shared__ float red[kSoftmaxThreads / 32];
   const float* xr = x + (long long)blockIdx.x * ldx;
   __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;
@@ -120,7 +122,7 @@ static inline int grid_for_vae(long long n, int threads) {
 using namespace ttvdm;
 
 extern "C" int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, int rows, int cols, int cols_out,
-                                  void* stream_) {
+                                  int causal, void* stream_) {
   if (int rc = ensure_init()) return rc;
   if (!x || !out || rows <= 0 || cols <= 0 || cols_out < cols || ldx < cols || ldo < cols_out)
     return fail(TTVDM_ERR_SHAPE, "softmax_rows: rows=%d cols=%d cols_out=%d ldx=%d ldo=%d", rows, cols, cols_out, ldx, ldo);
@@ -136,10 +138,10 @@ extern "C" int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, i
       attr = true;
     }
     softmax_rows_kernel<true><<<rows, kSoftmaxThreads, smem, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(out), ldo,
-                                                                      cols, cols_out);
+                                                                      cols, cols_out, causal);
   } else {
     softmax_rows_kernel<false><<<rows, kSoftmaxThreads, 0, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(out), ldo,
-                                                                    cols, cols_out);
+                                                                    cols, cols_out, causal);
   }
   TTVDM_CHECK_LAUNCH("softmax_rows_kernel");
   return 0;

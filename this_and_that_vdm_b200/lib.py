@@ -113,6 +113,7 @@ EXPORTS = [
     "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
     "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step", "ttvdm_gesture_raster",
     "ttvdm_softmax_rows", "ttvdm_im2col_s2_pad01", "ttvdm_vae_time_conv_out",
+    "ttvdm_act_inplace", "ttvdm_layernorm_flat",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -343,11 +344,12 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
 
 
 # ---- VAE-only entry points (include/ttvdm.h, "VAE either side of the loop")
-def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out) -> None:
-    """x fp32 [rows, cols] (ldx) -> out bf16 [rows, cols_out] (ldo); columns >= cols are written as zeros."""
+def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out, causal=False) -> None:
+    """x fp32 [rows, cols] (ldx) -> out bf16 [rows, cols_out] (ldo); columns >= cols are written as zeros; causal: row r
+    attends to columns 0..r only."""
     if x.dtype != torch.float32 or out.dtype != torch.bfloat16:
         raise TtvdmError("softmax_rows: x must be fp32 and out bf16")
-    call_raw("ttvdm_softmax_rows", c_void_p(_ptr(x)), ldx, c_void_p(_ptr(out)), ldo, rows, cols, cols_out)
+    call_raw("ttvdm_softmax_rows", c_void_p(_ptr(x)), ldx, c_void_p(_ptr(out)), ldo, rows, cols, cols_out, int(bool(causal)))
 
 
 def im2col_s2_pad01(x, out, *, n_img, H, W, C) -> None:
@@ -364,3 +366,19 @@ def vae_time_conv_out(x, w, bias, out, *, B, F, H, W, ldx) -> None:
     w, bias = w.contiguous(), bias.contiguous()
     call_raw("ttvdm_vae_time_conv_out", c_void_p(_ptr(x)), ldx, c_void_p(w.data_ptr()), c_void_p(bias.data_ptr()),
              c_void_p(_ptr(out)), B, F, H * W)
+
+
+# ---- conditioning-builder entry points (include/ttvdm.h, "Conditioning builder")
+ACT_GELU, ACT_QUICK_GELU = 2, 3
+
+
+def act_inplace(x, kind: int) -> None:
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise TtvdmError("act_inplace: x must be a contiguous bf16 tensor")
+    call_raw("ttvdm_act_inplace", c_void_p(_ptr(x)), c_size_t(x.numel()), kind)
+
+
+def layernorm_flat(x, out, *, rows, n, eps=1e-5) -> None:
+    if x.dtype != torch.float32 or out.dtype != torch.float32 or not x.is_contiguous() or not out.is_contiguous():
+        raise TtvdmError("layernorm_flat: x / out must be contiguous fp32 tensors")
+    call_raw("ttvdm_layernorm_flat", c_void_p(_ptr(x)), c_void_p(_ptr(out)), rows, c_size_t(n), c_float(eps))

@@ -288,18 +288,37 @@ class VaeEngine:
         x[..., :C] = t.permute(0, 2, 3, 1)
         return x.view(N * H * W, pad_to)
 
-    def encode(self, x: torch.Tensor, max_images_per_pass: int = 4) -> torch.Tensor:
-        """x [N, 3, H, W] in [-1, 1] -> moments [N, 2*latent, H/f, W/f] in x.dtype (mean | logvar, after quant_conv)."""
+    def encode(self, x: torch.Tensor, max_images_per_pass: int = 4, dedupe: bool = True) -> torch.Tensor:
+        """x [N, 3, H, W] in [-1, 1] -> moments [N, 2*latent, H/f, W/f] in x.dtype (mean | logvar, after quant_conv).
+        dedupe: bit-identical images are encoded once (the encoder has no cross-image op) — 12 of the 14 gesture
+        condition frames of the reference are all-zero images (data_loader/video_this_that_dataset.py:28-130)."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected an image batch [N, 3, H, W], got {tuple(x.shape)}")
         n_down = sum(1 for b in self.e_down if b["down_w"] is not None)
         N, _, H, W = x.shape
         if H % (1 << n_down) or W % (1 << n_down):
             raise ValueError(f"image height / width must be multiples of {1 << n_down}, got {H}x{W}")
+        inverse = None
+        if dedupe and N > 1:
+            flat = x.reshape(N, -1)
+            first = [0]  # index of the first occurrence of every distinct image, in order of appearance
+            inv = [0] * N
+            for i in range(1, N):
+                for u, j in enumerate(first):
+                    if torch.equal(flat[i], flat[j]):
+                        inv[i] = u
+                        break
+                else:
+                    inv[i] = len(first)
+                    first.append(i)
+            if len(first) < N:
+                inverse = torch.tensor(inv, device=x.device)
+                x = x[torch.tensor(first, device=x.device)]
         outs = []
-        for i0 in range(0, N, max_images_per_pass):
+        for i0 in range(0, x.shape[0], max_images_per_pass):
             outs.append(self._encode_pass(x[i0:i0 + max_images_per_pass]))
-        return torch.cat(outs, 0).to(x.dtype)
+        mom = torch.cat(outs, 0).to(x.dtype)
+        return mom if inverse is None else mom[inverse]
 
     def _encode_pass(self, x: torch.Tensor) -> torch.Tensor:
         n, _, H, W = x.shape
