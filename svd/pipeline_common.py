@@ -159,21 +159,21 @@ class SVDPipelineBase:
             image = self._pil_to_pt(image) * 2.0 - 1.0
             image = _gaussian_blur_resize(image, (224, 224))
             image = (image + 1.0) / 2.0
-            image = self.feature_extractor(images=image, do_normalize=True, do_center_crop=False, do_resize=False,
-                                           do_rescale=False, return_tensors="pt").pixel_values
+            if self.feature_extractor is not None:
+                image = self.feature_extractor(images=image, do_normalize=True, do_center_crop=False, do_resize=False,
+                                               do_rescale=False, return_tensors="pt").pixel_values
+            else:  # CLIPImageProcessor defaults (the SVD repo's feature_extractor/preprocessor_config.json)
+                mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+                std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+                image = (image - mean) / std
         image = image.to(device=device, dtype=dtype)
-        emb = self.image_encoder(image).image_embeds.unsqueeze(1)
-        bs, seq_len, _ = emb.shape
-        ehs = emb.repeat(1, num_videos_per_prompt, 1).view(bs * num_videos_per_prompt, seq_len, -1)
-        if use_text:
-            text = text_encoder(prompt)[0]
-            ehs = torch.cat((text, ehs), dim=1)
-            ln = nn.LayerNorm((ehs.shape[1], ehs.shape[2])).to(device=device, dtype=dtype)  # fresh, weight 1 / bias 0
-            ehs = ln(ehs)
-        if do_classifier_free_guidance:
-            neg = torch.zeros_like(ehs)
-            ehs = torch.cat([ehs, neg, neg]) if use_instructpix2pix else torch.cat([neg, ehs])
-        return ehs
+        emb = self.image_encoder(image).image_embeds
+        text = text_encoder(prompt)[0] if use_text else None
+        # tail of encode_clip (:156-186): [text | image] concat, fresh LayerNorm((78, 1024)), CFG zero stack — on the
+        # sm_100a kernels (ttvdm_layernorm_flat), fp32 result cast to the towers' dtype like the reference's
+        from this_and_that_vdm_b200.clip_engine import assemble_conditioning
+        return assemble_conditioning(emb, text, do_classifier_free_guidance, num_videos_per_prompt,
+                                     use_instructpix2pix).to(dtype)
 
     def _encode_vae_image(self, image, device, num_videos_per_prompt, do_classifier_free_guidance,
                           use_instructpix2pix=False):
@@ -232,13 +232,19 @@ class SVDPipelineBase:
 
     @staticmethod
     def _tensor2vid(video: torch.Tensor, output_type="pil"):
-        """[B, C, F, H, W] in [-1, 1] -> per batch list of frames (np / pil)."""
+        """tensor2vid of the reference (:53-65): [B, C, F, H, W] in [-1, 1] -> per batch element
+        VaeImageProcessor.postprocess(frames [F, C, H, W], output_type): "pt" tensor in [0, 1], "np" [F, H, W, C],
+        "pil" list of images."""
         outs = []
         for vid in video:
-            frames = (vid.permute(1, 2, 3, 0) / 2 + 0.5).clamp(0, 1).cpu().float().numpy()
+            frames = (vid.permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+            if output_type == "pt":
+                outs.append(frames)
+                continue
+            arr = frames.cpu().permute(0, 2, 3, 1).float().numpy()
             if output_type == "pil":
-                frames = [PIL.Image.fromarray((f * 255).round().astype("uint8")) for f in frames]
-            outs.append(frames)
+                arr = [PIL.Image.fromarray((f * 255).round().astype("uint8")) for f in arr]
+            outs.append(arr)
         return outs
 
     # ---- the hot loop

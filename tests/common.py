@@ -96,3 +96,60 @@ def vae_inputs(n_frames: int, lh: int, lw: int, n_images: int = 2, seed: int = 5
     z = torch.randn(n_frames, 4, lh, lw, generator=g)
     x = torch.rand(n_images, 3, 8 * lh, 8 * lw, generator=g) * 2.0 - 1.0
     return z, x
+
+
+# ---- CLIP towers (HF key names); weights are generated here from a seed so that no test needs `transformers`
+TINY_CLIP_VISION = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                        image_size=56, patch_size=14, projection_dim=64, hidden_act="gelu")
+TINY_CLIP_VISION_D80 = dict(hidden_size=320, intermediate_size=640, num_hidden_layers=2, num_attention_heads=4,
+                            image_size=42, patch_size=14, projection_dim=64, hidden_act="quick_gelu")  # head_dim 80 (ViT-H)
+TINY_CLIP_TEXT = dict(vocab_size=300, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                      num_attention_heads=2, max_position_embeddings=77, hidden_act="gelu")
+
+
+def _clip_layers(sd, prefix, cfg, g):
+    C, I = cfg["hidden_size"], cfg["intermediate_size"]
+    rn = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale  # noqa: E731
+    for i in range(cfg["num_hidden_layers"]):
+        p = f"{prefix}.encoder.layers.{i}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[f"{p}.self_attn.{n}.weight"] = rn(C, C, scale=C ** -0.5)
+            sd[f"{p}.self_attn.{n}.bias"] = rn(C, scale=0.1)
+        for n in ("layer_norm1", "layer_norm2"):
+            sd[f"{p}.{n}.weight"] = 1.0 + rn(C, scale=0.1)
+            sd[f"{p}.{n}.bias"] = rn(C, scale=0.1)
+        sd[f"{p}.mlp.fc1.weight"], sd[f"{p}.mlp.fc1.bias"] = rn(I, C, scale=C ** -0.5), rn(I, scale=0.1)
+        sd[f"{p}.mlp.fc2.weight"], sd[f"{p}.mlp.fc2.bias"] = rn(C, I, scale=I ** -0.5), rn(C, scale=0.1)
+
+
+def clip_vision_sd(cfg: dict, seed: int = 77):
+    g = torch.Generator().manual_seed(seed)
+    C, ps = cfg["hidden_size"], cfg["patch_size"]
+    n_pos = (cfg["image_size"] // ps) ** 2 + 1
+    rn = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale  # noqa: E731
+    sd = {"vision_model.embeddings.class_embedding": rn(C),
+          "vision_model.embeddings.patch_embedding.weight": rn(C, 3, ps, ps, scale=(3 * ps * ps) ** -0.5),
+          "vision_model.embeddings.position_embedding.weight": rn(n_pos, C, scale=0.3)}
+    for n in ("pre_layrnorm", "post_layernorm"):
+        sd[f"vision_model.{n}.weight"], sd[f"vision_model.{n}.bias"] = 1.0 + rn(C, scale=0.1), rn(C, scale=0.1)
+    _clip_layers(sd, "vision_model", cfg, g)
+    sd["visual_projection.weight"] = rn(cfg["projection_dim"], C, scale=C ** -0.5)
+    return sd
+
+
+def clip_text_sd(cfg: dict, seed: int = 78):
+    g = torch.Generator().manual_seed(seed)
+    C = cfg["hidden_size"]
+    rn = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale  # noqa: E731
+    sd = {"text_model.embeddings.token_embedding.weight": rn(cfg["vocab_size"], C, scale=0.5),
+          "text_model.embeddings.position_embedding.weight": rn(cfg["max_position_embeddings"], C, scale=0.3),
+          "text_model.final_layer_norm.weight": 1.0 + rn(C, scale=0.1), "text_model.final_layer_norm.bias": rn(C, scale=0.1)}
+    _clip_layers(sd, "text_model", cfg, g)
+    return sd
+
+
+def clip_inputs(vcfg: dict, tcfg: dict, n: int = 1, seed: int = 9):
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(n, 3, vcfg["image_size"], vcfg["image_size"], generator=g)
+    ids = torch.randint(0, tcfg["vocab_size"], (n, tcfg["max_position_embeddings"]), generator=g)
+    return px, ids

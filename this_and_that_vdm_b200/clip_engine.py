@@ -1,0 +1,210 @@
+"""B200 execution engine of the conditioning builder (scope table row "next #2"): encode_clip of the reference
+(svd/pipeline_stable_video_diffusion_controlnet.py:130-188, same in svd/pipeline_stable_video_diffusion.py).
+
+  * ClipTowerEngine(kind="vision") — transformers CLIPVisionModelWithProjection(pixel_values).image_embeds  (:155)
+  * ClipTowerEngine(kind="text")   — transformers CLIPTextModel(input_ids)[0] (causal)                      (:166)
+  * assemble_conditioning          — [text | image] concat, fresh LayerNorm((78, 1024)), CFG zero stack     (:156-186)
+
+Kernel schedule per encoder layer (tokens are a bf16 matrix [N*S, C], rows ordered (image, token)):
+  LayerNorm -> Q for all heads in one GEMM (head dims zero-padded to a multiple of 64: ViT-H has 16 heads of 80) ->
+  per (image, head): K_h = gemm(y, Wk_h), V_h^T = gemm(Wv_h, y) (operands swapped: no transpose pass),
+  scores = gemm(Q_h, K_h) in fp32, ttvdm_softmax_rows (causal for the text tower), out = gemm(P, V_h^T) + b_v ->
+  out_proj GEMM with the residual in its epilogue -> LayerNorm -> fc1 GEMM -> ttvdm_act_inplace -> fc2 GEMM + residual.
+The towers run once per video (257 / 77 tokens): they are launch-count bound, not roofline bound; what matters is that
+the conditioning is produced on the device, in the layout the denoiser consumes, with no library dispatch.
+
+torch owns device memory and does pure data movement (patch unfold, embedding-row gather, concat); all arithmetic is
+in libttvdm_sm100.so. No CPU / eager fallback exists.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib
+from .engine import BF16, _bf, _f32
+
+_ACTS = {"gelu": lib.ACT_GELU, "quick_gelu": lib.ACT_QUICK_GELU}
+
+
+def _pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+class ClipTowerEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config, kind: str, device):
+        lib.init()
+        if kind not in ("vision", "text"):
+            raise ValueError(kind)
+        self.kind, self.device = kind, torch.device(device)
+        get = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
+        self.C, self.I = int(get("hidden_size")), int(get("intermediate_size"))
+        self.H = int(get("num_attention_heads"))
+        self.eps = float(get("layer_norm_eps", 1e-5))
+        act = get("hidden_act", "quick_gelu")
+        if act not in _ACTS:
+            raise lib.TtvdmError(f"sm_100a CLIP engine supports hidden_act gelu / quick_gelu (got {act!r})")
+        self.act = _ACTS[act]
+        if self.C % 64 or self.I % 64 or self.C % self.H or (self.C // self.H) % 8:
+            raise lib.TtvdmError(f"sm_100a CLIP engine needs hidden/intermediate sizes %% 64 == 0 and head_dim %% 8 == 0 "
+                                 f"(got hidden {self.C}, intermediate {self.I}, heads {self.H})")
+        self.d = self.C // self.H
+        self.dp = _pad64(self.d)
+        self.patch = int(get("patch_size", 0) or 0)
+        self._pack({k: v for k, v in state_dict.items()})
+
+    # ============================================================================================ packing
+    def _pack(self, sd) -> None:
+        dev, C, H, d, dp = self.device, self.C, self.H, self.d, self.dp
+        pre = "vision_model" if self.kind == "vision" else "text_model"
+
+        def pad_heads(w: torch.Tensor, b: torch.Tensor):
+            wp = torch.zeros(H * dp, C, dtype=torch.float32)
+            bp = torch.zeros(H * dp, dtype=torch.float32)
+            wp.view(H, dp, C)[:, :d] = w.detach().float().cpu().view(H, d, C)
+            bp.view(H, dp)[:, :d] = b.detach().float().cpu().view(H, d)
+            return _bf(wp, dev), _f32(bp, dev)
+
+        self.layers: List[dict] = []
+        i = 0
+        while f"{pre}.encoder.layers.{i}.layer_norm1.weight" in sd:
+            p = f"{pre}.encoder.layers.{i}"
+            L = {}
+            for n in ("layer_norm1", "layer_norm2"):
+                L[n] = (_f32(sd[f"{p}.{n}.weight"], dev), _f32(sd[f"{p}.{n}.bias"], dev))
+            L["wq"], L["bq"] = pad_heads(sd[f"{p}.self_attn.q_proj.weight"], sd[f"{p}.self_attn.q_proj.bias"])
+            L["wk"], L["bk"] = pad_heads(sd[f"{p}.self_attn.k_proj.weight"], sd[f"{p}.self_attn.k_proj.bias"])
+            L["wv"] = _bf(sd[f"{p}.self_attn.v_proj.weight"], dev)
+            # + 128 zeros: the epilogue of the last head's 64-column tile may read bias columns past C
+            L["bv"] = _f32(torch.cat([sd[f"{p}.self_attn.v_proj.bias"].detach().float().cpu(), torch.zeros(128)]), dev)
+            L["wo"], L["bo"] = _bf(sd[f"{p}.self_attn.out_proj.weight"], dev), _f32(sd[f"{p}.self_attn.out_proj.bias"], dev)
+            L["w1"], L["b1"] = _bf(sd[f"{p}.mlp.fc1.weight"], dev), _f32(sd[f"{p}.mlp.fc1.bias"], dev)
+            L["w2"], L["b2"] = _bf(sd[f"{p}.mlp.fc2.weight"], dev), _f32(sd[f"{p}.mlp.fc2.bias"], dev)
+            self.layers.append(L)
+            i += 1
+        if self.kind == "vision":
+            w = sd[f"{pre}.embeddings.patch_embedding.weight"].detach().float().cpu()
+            k = w[0].numel()
+            self.kp = _pad64(k)
+            wp = torch.zeros(C, self.kp)
+            wp[:, :k] = w.reshape(C, k)
+            self.w_patch = _bf(wp, dev)
+            pos = sd[f"{pre}.embeddings.position_embedding.weight"].detach().float().cpu()
+            self.cls_pos0 = _bf(sd[f"{pre}.embeddings.class_embedding"].detach().float().cpu() + pos[0], dev)
+            self.pos_rest = _bf(pos[1:], dev)
+            self.pre_ln = (_f32(sd[f"{pre}.pre_layrnorm.weight"], dev), _f32(sd[f"{pre}.pre_layrnorm.bias"], dev))
+            self.post_ln = (_f32(sd[f"{pre}.post_layernorm.weight"], dev), _f32(sd[f"{pre}.post_layernorm.bias"], dev))
+            self.w_proj = _bf(sd["visual_projection.weight"], dev)
+        else:
+            self.tok_emb = _bf(sd[f"{pre}.embeddings.token_embedding.weight"], dev)
+            self.pos_emb = _bf(sd[f"{pre}.embeddings.position_embedding.weight"], dev)
+            self.final_ln = (_f32(sd[f"{pre}.final_layer_norm.weight"], dev), _f32(sd[f"{pre}.final_layer_norm.bias"], dev))
+
+    # ============================================================================================ helpers
+    def _empty(self, *shape, dtype=BF16) -> torch.Tensor:
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def _linear(self, a, w, *, M, bias=None, res1=None, out=None, out_fp32=False):
+        N, K = w.shape
+        if out is None:
+            out = self._empty(M, N, dtype=torch.float32 if out_fp32 else BF16)
+        lib.gemm(a, w, out, M=M, N=N, k1=K, bias=bias, res1=res1, out_fp32=out_fp32)
+        return out
+
+    def _ln(self, x, gb, rows):
+        out = self._empty(rows, self.C)
+        lib.layernorm(x, out, gb[0], gb[1], rows=rows, C=self.C, eps=self.eps)
+        return out
+
+    def _encoder(self, x: torch.Tensor, N: int, S: int, causal: bool) -> torch.Tensor:
+        """x bf16 [N*S, C] -> same, through all encoder layers (in place)."""
+        C, H, d, dp = self.C, self.H, self.d, self.dp
+        rows = N * S
+        Sp = _pad64(S)
+        scale = float(d) ** -0.5
+        scores = self._empty(S, S, dtype=torch.float32)
+        probs = self._empty(S, Sp)
+        k_h = self._empty(S, dp)
+        vt = torch.zeros(d, Sp, dtype=BF16, device=self.device)  # columns >= S stay zero (K padding of P V)
+        o = self._empty(rows, C)
+        for L in self.layers:
+            y = self._ln(x, L["layer_norm1"], rows)
+            q = self._linear(y, L["wq"], M=rows, bias=L["bq"])  # [rows, H*dp], padded head dims are exact zeros
+            for n in range(N):
+                yn = y[n * S:(n + 1) * S]
+                for h in range(H):
+                    lib.gemm(yn, L["wk"][h * dp:(h + 1) * dp], k_h, M=S, N=dp, k1=C, bias=L["bk"][h * dp:])
+                    lib.gemm(L["wv"][h * d:(h + 1) * d], yn, vt, M=d, N=S, k1=C, ldo=Sp)
+                    lib.gemm(q[n * S:, h * dp:], k_h, scores, M=S, N=S, k1=dp, lda=H * dp, s0=scale, out_fp32=True)
+                    lib.softmax_rows(scores, probs, rows=S, cols=S, ldx=S, ldo=Sp, cols_out=Sp, causal=causal)
+                    lib.gemm(probs, vt, o[n * S:, h * d:], M=S, N=d, k1=Sp, bias=L["bv"][h * d:], ldo=C)
+            self._linear(o, L["wo"], M=rows, bias=L["bo"], res1=x, out=x)
+            y = self._ln(x, L["layer_norm2"], rows)
+            hdn = self._linear(y, L["w1"], M=rows, bias=L["b1"])
+            lib.act_inplace(hdn, self.act)
+            self._linear(hdn, L["w2"], M=rows, bias=L["b2"], res1=x, out=x)
+        return x
+
+    # ============================================================================================ towers
+    def image_embeds(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """[N, 3, H, W] (already CLIP-normalised) -> fp32 [N, projection_dim]."""
+        if self.kind != "vision":
+            raise lib.TtvdmError("image_embeds() needs a vision tower")
+        if pixel_values.device != self.device:
+            raise lib.TtvdmError(f"pixel_values on {pixel_values.device}, tower on {self.device}")
+        N, ch, Hh, Ww = pixel_values.shape
+        ps = self.patch
+        gh, gw = Hh // ps, Ww // ps
+        P = gh * gw
+        if ch != 3 or P != self.pos_rest.shape[0]:
+            raise ValueError(f"expected [N, 3, {ps}*g, {ps}*g] with {self.pos_rest.shape[0]} patches, got "
+                             f"{tuple(pixel_values.shape)}")
+        S = P + 1
+        # non-overlapping patches -> rows (n, gy, gx), columns (c, ky, kx): pure data movement
+        patches = torch.zeros(N * P, self.kp, dtype=BF16, device=self.device)
+        pv = pixel_values[:, :, :gh * ps, :gw * ps].reshape(N, 3, gh, ps, gw, ps).permute(0, 2, 4, 1, 3, 5)
+        patches[:, :3 * ps * ps] = pv.reshape(N * P, 3 * ps * ps)
+        tok = self._empty(N * S, self.C)
+        tok.view(N, S, self.C)[:, 0] = self.cls_pos0
+        for n in range(N):
+            lib.gemm(patches[n * P:(n + 1) * P], self.w_patch, tok[n * S + 1:], M=P, N=self.C, k1=self.kp,
+                     res1=self.pos_rest, s1=1.0)
+        x = self._ln(tok, self.pre_ln, N * S)
+        x = self._encoder(x, N, S, causal=False)
+        pooled = x.view(N, S, self.C)[:, 0].contiguous()
+        pooled = self._ln(pooled, self.post_ln, N)
+        return self._linear(pooled, self.w_proj, M=N, out_fp32=True)
+
+    def last_hidden_state(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """[B, L] token ids -> fp32 [B, L, hidden] (CLIPTextModel(...)[0])."""
+        if self.kind != "text":
+            raise lib.TtvdmError("last_hidden_state() needs a text tower")
+        B, L = input_ids.shape
+        if L > self.pos_emb.shape[0]:
+            raise ValueError(f"sequence length {L} exceeds max_position_embeddings {self.pos_emb.shape[0]}")
+        rows = self.tok_emb.index_select(0, input_ids.reshape(-1).to(self.device))  # gather: data movement
+        x = self._empty(B * L, self.C)
+        for b in range(B):
+            lib.axpy(rows[b * L:(b + 1) * L], self.pos_emb, x[b * L:(b + 1) * L], 1.0, L * self.C)
+        x = self._encoder(x, B, L, causal=True)
+        return self._ln(x, self.final_ln, B * L).view(B, L, self.C).float()
+
+
+def assemble_conditioning(image_embeds: torch.Tensor, text_states: Optional[torch.Tensor], do_cfg: bool,
+                          num_videos_per_prompt: int = 1, use_instructpix2pix: bool = False) -> torch.Tensor:
+    """Tail of encode_clip (:156-186): image token appended AFTER the text tokens, a fresh LayerNorm over the whole
+    (tokens, dim) slab of every sample (ttvdm_layernorm_flat: weight 1, bias 0, eps 1e-5) — only when text is used —
+    and the CFG zero stack. Returns fp32 [B(*2), tokens, dim]."""
+    ehs = image_embeds.unsqueeze(1)
+    bs, seq, _ = ehs.shape
+    ehs = ehs.repeat(1, num_videos_per_prompt, 1).view(bs * num_videos_per_prompt, seq, -1)
+    if text_states is not None:
+        slab = torch.cat((text_states.to(torch.float32), ehs.to(torch.float32)), dim=1).contiguous()
+        out = torch.empty_like(slab)
+        lib.layernorm_flat(slab, out, rows=slab.shape[0], n=slab.shape[1] * slab.shape[2], eps=1e-5)
+        ehs = out
+    if do_cfg:
+        neg = torch.zeros_like(ehs)
+        ehs = torch.cat([ehs, neg, neg]) if use_instructpix2pix else torch.cat([neg, ehs])
+    return ehs
