@@ -67,6 +67,8 @@ class _Node(nn.Module):
 class _TowerBase(nn.Module):
     _kind = ""
     _defaults: dict = {}
+    # replay each tower as one CUDA graph per input shape (TTVDM_CLIP_GRAPH=0 launches kernel by kernel)
+    use_cuda_graph = os.environ.get("TTVDM_CLIP_GRAPH", "1") != "0"
 
     def __init__(self, config=None, **kwargs):
         super().__init__()
@@ -191,7 +193,7 @@ class CLIPVisionModelWithProjection(_TowerBase):
     def forward(self, pixel_values: torch.Tensor = None, **_unused):
         if pixel_values is None:
             raise ValueError("You have to specify pixel_values")
-        emb = self._get_engine().image_embeds(pixel_values)
+        emb = self._get_engine().image_embeds(pixel_values, use_graph=self.use_cuda_graph)
         return _Output(image_embeds=emb.to(pixel_values.dtype if pixel_values.is_floating_point() else self.dtype))
 
 
@@ -204,5 +206,5 @@ class CLIPTextModel(_TowerBase):
     def forward(self, input_ids: torch.Tensor = None, **_unused):
         if input_ids is None:
             raise ValueError("You have to specify input_ids")
-        hs = self._get_engine().last_hidden_state(input_ids)
+        hs = self._get_engine().last_hidden_state(input_ids, use_graph=self.use_cuda_graph)
         return _Output(last_hidden_state=hs.to(self.dtype))

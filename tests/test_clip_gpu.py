@@ -103,3 +103,21 @@ def test_vit_h_shaped_layers_and_assembly():
         ehs = assemble_conditioning(out, txt.cuda(), True)
     want = CO.assemble(ref, txt, True)
     assert ehs.shape == (2, 78, 1024) and float(ehs[0].abs().max()) == 0.0 and rel_l2(ehs, want) < CAP
+
+
+def test_cuda_graph_replay_equals_kernel_by_kernel():
+    """The drop-in towers replay one CUDA graph per input shape; the result must be bit-identical to launching the same
+    kernels one by one, also for a second input of the same shape (static input buffer is refreshed)."""
+    from this_and_that_vdm_b200.clip_engine import ClipTowerEngine
+    cfg = TINY_CLIP_VISION_D80
+    eng = ClipTowerEngine(clip_vision_sd(cfg), cfg, "vision", "cuda:0")
+    px, ids = clip_inputs(cfg, TINY_CLIP_TEXT, n=2)
+    px2 = px.flip(0) * 0.5
+    teng = ClipTowerEngine(clip_text_sd(TINY_CLIP_TEXT), TINY_CLIP_TEXT, "text", "cuda:0")
+    with torch.no_grad():
+        for x in (px, px2, px):
+            assert torch.equal(eng.image_embeds(x.cuda(), use_graph=True), eng.image_embeds(x.cuda()))
+        ids2 = (ids + 3) % TINY_CLIP_TEXT["vocab_size"]
+        for i in (ids, ids2):
+            assert torch.equal(teng.last_hidden_state(i.cuda(), use_graph=True), teng.last_hidden_state(i.cuda()))
+    assert len(eng._graphs) == 1 and len(teng._graphs) == 1

@@ -65,6 +65,13 @@ def main():
         res["text_ms"] = timed(lambda: txt.last_hidden_state(idd))
         res["assemble_ms"] = timed(lambda: assemble_conditioning(emb, hs, True))
         res["total_ms"] = res["vision_ms"] + res["text_ms"] + res["assemble_ms"]
+        # the same towers replayed as one CUDA graph each (what the drop-in modules do by default)
+        eg = vis.image_embeds(pxd, use_graph=True)
+        hg = txt.last_hidden_state(idd, use_graph=True)
+        res["graph_equals_eager"] = bool(torch.equal(eg, emb) and torch.equal(hg, hs))
+        res["vision_graph_ms"] = timed(lambda: vis.image_embeds(pxd, use_graph=True))
+        res["text_graph_ms"] = timed(lambda: txt.last_hidden_state(idd, use_graph=True))
+        res["total_graph_ms"] = res["vision_graph_ms"] + res["text_graph_ms"] + res["assemble_ms"]
         if not a.no_cpu:
             torch.set_num_threads(os.cpu_count())
             t0 = time.time()
