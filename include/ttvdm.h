@@ -244,8 +244,9 @@ int ttvdm_gesture_raster(const ttvdm_gesture_params* p, void* stream);
  *  softmax_rows     : the mid-block Attention (ONE head of 512 dims over all H*W/64 tokens of a frame) is
  *                     scores = ttvdm_gemm(Q, K) (fp32, scaled), P = softmax_rows(scores), out = ttvdm_gemm(P, V^T).
  *                     x fp32 [rows, cols] (row stride ldx) -> out bf16 [rows, cols_out] (row stride ldo);
- *                     columns [cols, cols_out) are written as 0 (K padding of the following GEMM). causal = 1 (CLIP
- *                     text tower): row r only attends to columns 0..r, the rest are written as 0.
+ *                     columns [cols, cols_out) are written as 0 (K padding of the following GEMM). causal = P > 0 (CLIP
+ *                     text tower): rows come in blocks of P queries (one block per head); row r is query r % P and only
+ *                     attends to columns 0..r % P, the rest are written as 0. causal = 0: no mask.
  *  im2col_s2_pad01  : Downsample2D(padding=0) of the encoder = F.pad(x, (0,1,0,1)) + Conv2d(C, C, 3, stride 2):
  *                     gathers [n, H/2, W/2, 9*C] patches (tap-major, then channel) for a LINEAR GEMM.
  *  vae_time_conv_out: TemporalDecoder.time_conv_out = Conv3d(3, 3, (3,1,1), padding (1,0,0)) over the frames of each

@@ -211,8 +211,9 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
 # ---- VAE entry points (include/ttvdm.h "VAE" section)
 def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out, causal=False) -> None:
     sc = _mat(x, rows, cols, ldx).float()
-    if causal:
-        sc = sc.masked_fill(torch.arange(cols)[None, :] > torch.arange(rows)[:, None], float("-inf"))
+    period = rows if causal is True else int(causal)
+    if period:
+        sc = sc.masked_fill(torch.arange(cols)[None, :] > (torch.arange(rows) % period)[:, None], float("-inf"))
     p = torch.softmax(sc, -1)
     o = torch.zeros(rows, cols_out)
     o[:, :cols] = p

@@ -41,6 +41,11 @@ def test_conditioning_kernels_vs_torch():
     want = torch.softmax(sc.masked_fill(torch.ones(S, S, dtype=torch.bool, device="cuda").triu(1), float("-inf")), -1)
     assert torch.allclose(pr[:, :S].float(), want, atol=4e-3, rtol=1e-2) and float(pr[:, S:].abs().max()) == 0.0
     assert float(pr[0, 0]) == 1.0 and float(pr[5, 6:].abs().max()) == 0.0
+    # blocks of queries (one block per head): row r is query r % period
+    sc2 = torch.cat([sc, sc * 0.5])
+    pr2 = torch.empty(2 * S, Sp, dtype=torch.bfloat16, device="cuda")
+    lib.softmax_rows(sc2, pr2, rows=2 * S, cols=S, ldx=S, ldo=Sp, cols_out=Sp, causal=S)
+    assert torch.equal(pr2[:S], pr) and float(pr2[S, 0]) == 1.0 and float(pr2[S + 5, 6:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("name,cfg", [("vision", TINY_CLIP_VISION), ("vision_d80", TINY_CLIP_VISION_D80)])
@@ -121,3 +126,18 @@ def test_cuda_graph_replay_equals_kernel_by_kernel():
         for i in (ids, ids2):
             assert torch.equal(teng.last_hidden_state(i.cuda(), use_graph=True), teng.last_hidden_state(i.cuda()))
     assert len(eng._graphs) == 1 and len(teng._graphs) == 1
+
+
+@pytest.mark.parametrize("kind", ["vision", "text"])
+def test_batched_heads_equal_the_per_head_schedule_on_gpu(kind):
+    from this_and_that_vdm_b200.clip_engine import ClipTowerEngine
+    cfg = TINY_CLIP_VISION_D80 if kind == "vision" else TINY_CLIP_TEXT
+    sd = clip_vision_sd(cfg) if kind == "vision" else clip_text_sd(cfg)
+    px, ids = clip_inputs(TINY_CLIP_VISION_D80, TINY_CLIP_TEXT, n=2)
+    eng = ClipTowerEngine(sd, cfg, kind, "cuda:0")
+    run = (lambda: eng.image_embeds(px.cuda())) if kind == "vision" else (lambda: eng.last_hidden_state(ids.cuda()))
+    with torch.no_grad():
+        a = run()
+        eng.batch_heads = False
+        b = run()
+    assert rel_l2(a, b) < 2e-3

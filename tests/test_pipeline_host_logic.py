@@ -50,6 +50,24 @@ def test_vision_tower_schedule_vs_oracle_and_transformers_golden(cfg):
     assert rel_l2(out, gold["vision" if cfg is TINY_CLIP_VISION else "vision_d80"]) < CAP
 
 
+@pytest.mark.parametrize("cfg,kind", [(TINY_CLIP_VISION_D80, "vision"), (TINY_CLIP_TEXT, "text")], ids=["vision", "text"])
+def test_batched_heads_equal_the_per_head_schedule(cfg, kind):
+    """Block-diagonal batching of the heads (one scores GEMM / softmax / P V GEMM per group of heads) must reproduce
+    the 5-launches-per-head schedule; the zero blocks contribute exact zeros."""
+    sd = clip_vision_sd(cfg) if kind == "vision" else clip_text_sd(cfg)
+    px, ids = clip_inputs(TINY_CLIP_VISION_D80, TINY_CLIP_TEXT, n=2)
+    with torch.no_grad(), fake_lib.installed():
+        eng = ClipTowerEngine(sd, cfg, kind, "cpu")
+        run = (lambda: eng.image_embeds(px)) if kind == "vision" else (lambda: eng.last_hidden_state(ids))
+        n0 = fake_lib.launch_count()
+        a = run()
+        n_batched = fake_lib.launch_count() - n0
+        eng.batch_heads = False
+        b = run()
+        n_per_head = fake_lib.launch_count() - n0 - n_batched
+    assert rel_l2(a, b) < 2e-3 and n_batched < n_per_head
+
+
 def test_text_tower_schedule_is_causal_and_matches_oracle():
     sd = clip_text_sd(TINY_CLIP_TEXT)
     _, ids = clip_inputs(TINY_CLIP_VISION, TINY_CLIP_TEXT, n=2)

@@ -53,6 +53,7 @@ class ClipTowerEngine:
         self.dp = _pad64(self.d)
         self.patch = int(get("patch_size", 0) or 0)
         self._graphs: Dict[tuple, tuple] = {}
+        self.batch_heads = True  # False: the 5-launches-per-head reference schedule (kept for A/B and tests)
         self._pack({k: v for k, v in state_dict.items()})
 
     # ============================================================================================ packing
@@ -120,6 +121,21 @@ class ClipTowerEngine:
 
     def _encoder(self, x: torch.Tensor, N: int, S: int, causal: bool) -> torch.Tensor:
         """x bf16 [N*S, C] -> same, through all encoder layers (in place)."""
+        rows = N * S
+        ws: dict = {}  # attention workspace, allocated (and zeroed where zeros matter) once per forward
+        for L in self.layers:
+            y = self._ln(x, L["layer_norm1"], rows)
+            o = self._attention_batched(L, y, N, S, causal, ws) if self.batch_heads else \
+                self._attention_per_head(L, y, N, S, causal)
+            self._linear(o, L["wo"], M=rows, bias=L["bo"], res1=x, out=x)
+            y = self._ln(x, L["layer_norm2"], rows)
+            hdn = self._linear(y, L["w1"], M=rows, bias=L["b1"])
+            lib.act_inplace(hdn, self.act)
+            self._linear(hdn, L["w2"], M=rows, bias=L["b2"], res1=x, out=x)
+        return x
+
+    def _attention_per_head(self, L, y, N: int, S: int, causal: bool) -> torch.Tensor:
+        """Reference schedule: 5 launches per (image, head)."""
         C, H, d, dp = self.C, self.H, self.d, self.dp
         rows = N * S
         Sp = _pad64(S)
@@ -129,23 +145,59 @@ class ClipTowerEngine:
         k_h = self._empty(S, dp)
         vt = torch.zeros(d, Sp, dtype=BF16, device=self.device)  # columns >= S stay zero (K padding of P V)
         o = self._empty(rows, C)
-        for L in self.layers:
-            y = self._ln(x, L["layer_norm1"], rows)
-            q = self._linear(y, L["wq"], M=rows, bias=L["bq"])  # [rows, H*dp], padded head dims are exact zeros
-            for n in range(N):
-                yn = y[n * S:(n + 1) * S]
-                for h in range(H):
-                    lib.gemm(yn, L["wk"][h * dp:(h + 1) * dp], k_h, M=S, N=dp, k1=C, bias=L["bk"][h * dp:])
-                    lib.gemm(L["wv"][h * d:(h + 1) * d], yn, vt, M=d, N=S, k1=C, ldo=Sp)
-                    lib.gemm(q[n * S:, h * dp:], k_h, scores, M=S, N=S, k1=dp, lda=H * dp, s0=scale, out_fp32=True)
-                    lib.softmax_rows(scores, probs, rows=S, cols=S, ldx=S, ldo=Sp, cols_out=Sp, causal=causal)
-                    lib.gemm(probs, vt, o[n * S:, h * d:], M=S, N=d, k1=Sp, bias=L["bv"][h * d:], ldo=C)
-            self._linear(o, L["wo"], M=rows, bias=L["bo"], res1=x, out=x)
-            y = self._ln(x, L["layer_norm2"], rows)
-            hdn = self._linear(y, L["w1"], M=rows, bias=L["b1"])
-            lib.act_inplace(hdn, self.act)
-            self._linear(hdn, L["w2"], M=rows, bias=L["b2"], res1=x, out=x)
-        return x
+        q = self._linear(y, L["wq"], M=rows, bias=L["bq"])  # [rows, H*dp], padded head dims are exact zeros
+        for n in range(N):
+            yn = y[n * S:(n + 1) * S]
+            for h in range(H):
+                lib.gemm(yn, L["wk"][h * dp:(h + 1) * dp], k_h, M=S, N=dp, k1=C, bias=L["bk"][h * dp:])
+                lib.gemm(L["wv"][h * d:(h + 1) * d], yn, vt, M=d, N=S, k1=C, ldo=Sp)
+                lib.gemm(q[n * S:, h * dp:], k_h, scores, M=S, N=S, k1=dp, lda=H * dp, s0=scale, out_fp32=True)
+                lib.softmax_rows(scores, probs, rows=S, cols=S, ldx=S, ldo=Sp, cols_out=Sp, causal=causal)
+                lib.gemm(probs, vt, o[n * S:, h * d:], M=S, N=d, k1=Sp, bias=L["bv"][h * d:], ldo=C)
+        return o
+
+    def _attention_batched(self, L, y, N: int, S: int, causal: bool, ws: dict) -> torch.Tensor:
+        """Heads batched into block-diagonal GEMMs: a launch of the persistent tcgen05 GEMM costs ~12 us on the device
+        whatever the problem size, and a head is a 257x257x80 problem. Per image and group of Hg heads:
+          Qbd [Hg*S, Hg*dp]  = block-diagonal copy of the group's queries (off-diagonal blocks are zeros), so ONE GEMM
+                               against K_g [S, Hg*dp] gives the scores of all Hg heads: rows (head, query), columns = keys;
+          softmax over all Hg*S rows in one launch (causal with period S for the text tower);
+          Pcat [S, Hg*Sp]    = probabilities regrouped per query; Vbd [Hg*d, Hg*Sp] = block-diagonal V^T, so ONE GEMM
+                               writes the group's output columns. The extra zero FLOPs (x Hg) are < 0.3 ms per tower.
+        Hg is the largest divisor of H with Hg*dp <= 1024 (8 for ViT-H, 16 for the SD-2.1 text tower)."""
+        C, H, d, dp = self.C, self.H, self.d, self.dp
+        rows = N * S
+        Sp = _pad64(S)
+        scale = float(d) ** -0.5
+        Hg = max(g for g in range(1, H + 1) if H % g == 0 and (g * dp <= 1024 or g == 1))
+        if not ws:
+            # the off-diagonal blocks of qbd / vbd and the columns >= S of vt are written once (zeros) and never again
+            ws["idx"] = torch.arange(Hg, device=self.device)
+            ws["qbd"] = torch.zeros(Hg * S, Hg * dp, dtype=BF16, device=self.device)
+            ws["vbd"] = torch.zeros(Hg * d, Hg * Sp, dtype=BF16, device=self.device)
+            ws["vt"] = torch.zeros(C, Sp, dtype=BF16, device=self.device)
+            ws["kg"] = self._empty(S, Hg * dp)
+            ws["scores"] = self._empty(Hg * S, S, dtype=torch.float32)
+            ws["probs"] = self._empty(Hg * S, Sp)
+            ws["pcat"] = self._empty(S, Hg * Sp)
+        idx, qbd, vbd, vt, kg = ws["idx"], ws["qbd"], ws["vbd"], ws["vt"], ws["kg"]
+        scores, probs, pcat = ws["scores"], ws["probs"], ws["pcat"]
+        o = self._empty(rows, C)
+        q = self._linear(y, L["wq"], M=rows, bias=L["bq"])  # [rows, H*dp], padded head dims are exact zeros
+        for n in range(N):
+            yn = y[n * S:(n + 1) * S]
+            lib.gemm(L["wv"], yn, vt, M=C, N=S, k1=C, ldo=Sp)  # V^T of all heads: [C, Sp]
+            qn = q[n * S:(n + 1) * S].view(S, H, dp)
+            for h0 in range(0, H, Hg):
+                lib.gemm(yn, L["wk"][h0 * dp:(h0 + Hg) * dp], kg, M=S, N=Hg * dp, k1=C, bias=L["bk"][h0 * dp:])
+                qbd.view(Hg, S, Hg, dp)[idx, :, idx, :] = qn[:, h0:h0 + Hg].permute(1, 0, 2)  # data movement
+                lib.gemm(qbd, kg, scores, M=Hg * S, N=S, k1=Hg * dp, s0=scale, out_fp32=True)
+                lib.softmax_rows(scores, probs, rows=Hg * S, cols=S, ldx=S, ldo=Sp, cols_out=Sp,
+                                 causal=S if causal else 0)
+                pcat.view(S, Hg, Sp).copy_(probs.view(Hg, S, Sp).permute(1, 0, 2))
+                vbd.view(Hg, d, Hg, Sp)[idx, :, idx, :] = vt[h0 * d:(h0 + Hg) * d].view(Hg, d, Sp)
+                lib.gemm(pcat, vbd, o[n * S:, h0 * d:], M=S, N=Hg * d, k1=Hg * Sp, bias=L["bv"][h0 * d:], ldo=C)
+        return o
 
     # ============================================================================================ towers
     def _replay(self, fn, x: torch.Tensor) -> torch.Tensor:

@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(kSoftmaxThreads)
 softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo, int cols_all,
                     int cols_out, int causal) {
   extern __shared__ float row[];
-  // causal (CLIP text tower): row r attends to keys 0..r; the masked probabilities are written as zeros
-  const int cols = causal ? min(cols_all, (int)blockIdx.x + 1) : cols_all;
+  // causal > 0 (CLIP text tower): rows come in blocks of `causal` queries (one block per head); query i = row % causal
+  // attends to keys 0..i; the masked probabilities are written as zeros
+  const int cols = causal > 0 ? min(cols_all, (int)(blockIdx.x % causal) + 1) : cols_all;
   __shared__ float red[kSoftmaxThreads / 32];
   const float* xr = x + (long long)blockIdx.x * ldx;
   __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;

@@ -345,11 +345,12 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
 
 # ---- VAE-only entry points (include/ttvdm.h, "VAE either side of the loop")
 def softmax_rows(x, out, *, rows, cols, ldx, ldo, cols_out, causal=False) -> None:
-    """x fp32 [rows, cols] (ldx) -> out bf16 [rows, cols_out] (ldo); columns >= cols are written as zeros; causal: row r
-    attends to columns 0..r only."""
+    """x fp32 [rows, cols] (ldx) -> out bf16 [rows, cols_out] (ldo); columns >= cols are written as zeros. causal: False /
+    0 = no mask; an int P = rows come in blocks of P queries, row r attends to columns 0..r % P; True = one block (P = rows)."""
+    causal = rows if causal is True else int(causal)
     if x.dtype != torch.float32 or out.dtype != torch.bfloat16:
         raise TtvdmError("softmax_rows: x must be fp32 and out bf16")
-    call_raw("ttvdm_softmax_rows", c_void_p(_ptr(x)), ldx, c_void_p(_ptr(out)), ldo, rows, cols, cols_out, int(bool(causal)))
+    call_raw("ttvdm_softmax_rows", c_void_p(_ptr(x)), ldx, c_void_p(_ptr(out)), ldo, rows, cols, cols_out, causal)
 
 
 def im2col_s2_pad01(x, out, *, n_img, H, W, C) -> None:
