@@ -1,6 +1,7 @@
 /*
  * ttvdm.h — C ABI of libttvdm_sm100.so: the hand-written sm_100a kernels behind the This&That / SVD
- * denoising hot path (UNetSpatioTemporalConditionModel + GestureNet ControlNetModel + Euler sampler).
+ * denoising hot path (UNetSpatioTemporalConditionModel + GestureNet ControlNetModel + Euler sampler) and, as the
+ * scope table's "next" rows, the gesture rasteriser, the VAE either side of the loop and the CLIP conditioning builder.
  *
  * The reference (Kiteretsu77/This_and_That_VDM) is 100 % Python and has no FFI of its own: every entry
  * point below replaces a *library-dispatched torch op class* on the hot path. Each declaration cites the

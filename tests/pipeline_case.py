@@ -84,3 +84,38 @@ def run_oracle(sds, seed=5):
     lat = randn_tensor((1, FRAMES, 4, H // 8, W // 8), generator=gen, dtype=torch.float32) * O.init_noise_sigma(sig)
     lat = O.denoise_loop(sds["unet"], cfg, lat, img_lat, ehs, ati, STEPS, 1.0, 3.0, sds["cn"], cfg, cond_lat, 1.0)
     return VO.decode_latents(sds["vae"], lat, FRAMES, decode_chunk_size=8), lat
+
+
+def run_vl_pipeline(mods, device, output_type="pt", seed=6):
+    """VL (UNet only) the way test_code/inference.py:108-145 calls it with use_text=False: the context is the single
+    CLIP image token (L = 1, no LayerNorm)."""
+    from svd.pipeline_stable_video_diffusion import StableVideoDiffusionPipeline
+    image, _, _ = inputs()
+    pipe = StableVideoDiffusionPipeline.from_pretrained(None, vae=mods["vae"], image_encoder=mods["vis"],
+                                                        unet=mods["unet"])
+    pipe.to(device)
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    out = pipe(image, prompt=None, use_text=False, text_encoder=None, height=H, width=W, num_frames=FRAMES,
+               num_inference_steps=STEPS, decode_chunk_size=14, fps=7, motion_bucket_id=127, noise_aug_strength=0.02,
+               generator=gen, output_type=output_type)
+    return out.frames
+
+
+def run_vl_oracle(sds, seed=6):
+    from svd.pipeline_common import randn_tensor
+    image, _, _ = inputs()
+    cfg = oracle_cfg(TINY)
+    px = torch.from_numpy(np.array(image).astype(np.float32) / 255.0).permute(2, 0, 1)[None]
+    clip_in = (CO.resize_with_antialiasing(px * 2 - 1, (224, 224)) + 1) / 2
+    emb = CO.vision_image_embeds(sds["vis"], (clip_in - MEAN) / STD, VISION["num_attention_heads"], "gelu")
+    ehs = CO.assemble(emb, None, do_cfg=True)  # [2, 1, 1024]
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    img = px * 2 - 1
+    img = img + 0.02 * randn_tensor(img.shape, generator=gen, dtype=img.dtype)
+    lat_img = VO.encode(sds["vae"], img)
+    img_lat = torch.cat([torch.zeros_like(lat_img), lat_img])[:, None].repeat(1, FRAMES, 1, 1, 1)
+    ati = torch.tensor([[6.0, 127.0, 0.02]] * 2)
+    sig = O.karras_sigmas(STEPS)
+    lat = randn_tensor((1, FRAMES, 4, H // 8, W // 8), generator=gen, dtype=torch.float32) * O.init_noise_sigma(sig)
+    lat = O.denoise_loop(sds["unet"], cfg, lat, img_lat, ehs, ati, STEPS, 1.0, 3.0)
+    return VO.decode_latents(sds["vae"], lat, FRAMES, decode_chunk_size=14)

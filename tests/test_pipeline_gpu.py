@@ -25,3 +25,12 @@ def test_vgl_pipeline_end_to_end_vs_oracles_on_gpu():
     want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert rel_l2(frames[0], want) < 5e-2
     assert len(pil) == 1 and len(pil[0]) == PC.FRAMES and pil[0][0].size == (PC.W, PC.H)
+
+
+def test_vl_pipeline_end_to_end_without_text_on_gpu():
+    mods, sds = PC.build("cuda")
+    with torch.no_grad():
+        frames = PC.run_vl_pipeline(mods, "cuda", output_type="pt")
+        ref = PC.run_vl_oracle(sds)
+    want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert frames[0].shape == want.shape and rel_l2(frames[0], want) < 5e-2

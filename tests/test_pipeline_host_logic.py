@@ -141,3 +141,13 @@ def test_vgl_pipeline_end_to_end_vs_oracles(cpu_engines):
     want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert rel_l2(frames[0], want) < 5e-2  # CLIP + VAE encode + 2 denoising steps + VAE decode chained in bf16 storage
     assert len(pil) == 1 and len(pil[0]) == PC.FRAMES and pil[0][0].size == (PC.W, PC.H)
+
+
+def test_vl_pipeline_end_to_end_without_text_vs_oracles(cpu_engines):
+    """StableVideoDiffusionPipeline (UNet only) with use_text=False: one context token, no LayerNorm, no GestureNet."""
+    mods, sds = PC.build("cpu")
+    with torch.no_grad(), fake_lib.installed():
+        frames = PC.run_vl_pipeline(mods, "cpu", output_type="pt")
+        ref = PC.run_vl_oracle(sds)
+    want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert frames[0].shape == want.shape and rel_l2(frames[0], want) < 5e-2

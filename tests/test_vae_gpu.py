@@ -44,6 +44,12 @@ def test_vae_only_kernels_vs_torch():
     want = torch.softmax(x[:, :cols].float(), -1)
     assert torch.allclose(out[:, :cols].float(), want, atol=4e-3, rtol=1e-2)
     assert float(out[:, cols:cols_out].abs().max()) == 0.0 and float(out[:, cols_out:].min()) == 7.0
+    # odd sizes / strides: the scalar path
+    x = (torch.randn(5, 41, generator=g) * 4).cuda()
+    out = torch.full((5, 67), 7.0, dtype=torch.bfloat16, device="cuda")
+    lib.softmax_rows(x, out, rows=5, cols=37, ldx=41, ldo=67, cols_out=64)
+    assert torch.allclose(out[:, :37].float(), torch.softmax(x[:, :37], -1), atol=4e-3, rtol=1e-2)
+    assert float(out[:, 37:64].abs().max()) == 0.0 and float(out[:, 64:].min()) == 7.0
     # a long row (re-read variant is only taken beyond 51200 columns; the cached one must hold 9216 = 72x128 tokens)
     x = (torch.randn(3, 9216, generator=g) * 3).cuda()
     out = torch.empty(3, 9216, dtype=torch.bfloat16, device="cuda")

@@ -28,12 +28,13 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red) 
 }
 
 // One CTA per row. CACHED: the row is staged in shared memory once (one HBM read per element); otherwise it is
-// re-read (rows longer than the shared-memory budget).
-template <bool CACHED>
+// re-read (rows longer than the shared-memory budget). VEC: 16-byte global loads / 8-byte stores (rows and strides
+// that are multiples of 4 elements on 16-byte aligned bases; the launcher checks).
+template <bool CACHED, bool VEC>
 __global__ void __launch_bounds__(kSoftmaxThreads)
 softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo, int cols_all,
                     int cols_out, int causal) {
-  extern __shared__ float row[];
+  extern __shared__ __align__(16) float row[];
   // causal > 0 (CLIP text tower): rows come in blocks of `causal` queries (one block per head); query i = row % causal
   // attends to keys 0..i; the masked probabilities are written as zeros
   const int cols = causal > 0 ? min(cols_all, (int)(blockIdx.x % causal) + 1) : cols_all;
@@ -41,10 +42,18 @@ softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* _
   const float* xr = x + (long long)blockIdx.x * ldx;
   __nv_bfloat16* orow = out + (long long)blockIdx.x * ldo;
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float v = __ldg(xr + c);
-    if (CACHED) row[c] = v;
-    m = fmaxf(m, v);
+  if (VEC) {  // CACHED is implied; cols == cols_all is a multiple of 4
+    for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
+      *reinterpret_cast<float4*>(row + c) = v;
+      m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+  } else {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      const float v = __ldg(xr + c);
+      if (CACHED) row[c] = v;
+      m = fmaxf(m, v);
+    }
   }
   m = block_reduce(m, true, red);
   constexpr float kLog2e = 1.4426950408889634f;
@@ -56,10 +65,18 @@ softmax_rows_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* _
   }
   s = block_reduce(s, false, red);
   const float inv = 1.f / s;
-  for (int c = threadIdx.x; c < cols_out; c += blockDim.x) {
-    float p = 0.f;
-    if (c < cols) p = (CACHED ? row[c] : exp2f((__ldg(xr + c) - m) * kLog2e)) * inv;
-    orow[c] = __float2bfloat16(p);
+  if (VEC) {  // cols_out is a multiple of 4 as well
+    for (int c = threadIdx.x * 4; c < cols_out; c += blockDim.x * 4) {
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < cols) p = *reinterpret_cast<const float4*>(row + c);
+      *reinterpret_cast<uint2*>(orow + c) = make_uint2(pack_bf16(p.x * inv, p.y * inv), pack_bf16(p.z * inv, p.w * inv));
+    }
+  } else {
+    for (int c = threadIdx.x; c < cols_out; c += blockDim.x) {
+      float p = 0.f;
+      if (c < cols) p = (CACHED ? row[c] : exp2f((__ldg(xr + c) - m) * kLog2e)) * inv;
+      orow[c] = __float2bfloat16(p);
+    }
   }
 }
 
@@ -130,19 +147,25 @@ extern "C" int ttvdm_softmax_rows(const float* x, int ldx, void* out, int ldo, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t smem = (size_t)cols * sizeof(float);
   constexpr size_t kMaxSmem = 200 * 1024;
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (smem <= kMaxSmem) {
     static bool attr = false;
     if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(softmax_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(softmax_rows_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kMaxSmem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(softmax_rows_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
       if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "softmax_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       attr = true;
     }
-    softmax_rows_kernel<true><<<rows, kSoftmaxThreads, smem, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(out), ldo,
-                                                                      cols, cols_out, causal);
+    const bool vec = causal == 0 && cols % 4 == 0 && cols_out % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    if (vec)
+      softmax_rows_kernel<true, true><<<rows, kSoftmaxThreads, smem, stream>>>(x, ldx, o, ldo, cols, cols_out, causal);
+    else
+      softmax_rows_kernel<true, false><<<rows, kSoftmaxThreads, smem, stream>>>(x, ldx, o, ldo, cols, cols_out, causal);
   } else {
-    softmax_rows_kernel<false><<<rows, kSoftmaxThreads, 0, stream>>>(x, ldx, static_cast<__nv_bfloat16*>(out), ldo,
-                                                                    cols, cols_out, causal);
+    softmax_rows_kernel<false, false><<<rows, kSoftmaxThreads, 0, stream>>>(x, ldx, o, ldo, cols, cols_out, causal);
   }
   TTVDM_CHECK_LAUNCH("softmax_rows_kernel");
   return 0;
