@@ -163,6 +163,9 @@ class DecoderOutput:
 
 class AutoencoderKLTemporalDecoder(ModelBase):
     _supports_gradient_checkpointing = True
+    # the pipelines skip diffusers' fp16 -> fp32 "force_upcast" dance for this class: the engine stores bf16 and
+    # accumulates in fp32 whatever the module dtype is, and every .to() would only trigger a weight re-pack
+    _ttvdm_native = True
 
     @register_to_config
     def __init__(

@@ -72,7 +72,8 @@ class StableVideoDiffusionPipeline(SVDPipelineBase):
             image_t = self._preprocess_image(image, height, width).to(device)
             noise = randn_tensor(image_t.shape, generator=generator, device=image_t.device, dtype=image_t.dtype)
             image_t = image_t + noise_aug_strength * noise
-            needs_upcasting = self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+            needs_upcasting = (self.vae.dtype == torch.float16 and self.vae.config.force_upcast
+                               and not getattr(self.vae, "_ttvdm_native", False))
             if needs_upcasting:
                 self.vae.to(dtype=torch.float32)
             img_lat = self._encode_vae_image(image_t, device, num_videos_per_prompt, do_cfg).to(ehs.dtype)

@@ -62,7 +62,7 @@ def run_pipeline(mods, device, output_type="pt", seed=5):
     return out.frames
 
 
-def run_oracle(sds, seed=5):
+def run_oracle(sds, seed=5, latent_dtype=torch.float32):
     """Same computation from oracle/: CLIP towers + assembly, VAE encode (first frame + gesture frames), 2 Euler steps of
     UNet + GestureNet with CFG, chunked VAE decode. Consumes the generator in the pipeline's order."""
     from svd.pipeline_common import randn_tensor
@@ -81,7 +81,8 @@ def run_oracle(sds, seed=5):
     cond_lat = VO.encode(sds["vae"], torch.from_numpy(cond).to(torch.float16).float())
     ati = torch.tensor([[6.0, 200.0, 0.02]] * 2)
     sig = O.karras_sigmas(STEPS)
-    lat = randn_tensor((1, FRAMES, 4, H // 8, W // 8), generator=gen, dtype=torch.float32) * O.init_noise_sigma(sig)
+    # the pipelines draw the initial noise in the conditioning's dtype (fp16 when the modules are fp16)
+    lat = randn_tensor((1, FRAMES, 4, H // 8, W // 8), generator=gen, dtype=latent_dtype).float() * O.init_noise_sigma(sig)
     lat = O.denoise_loop(sds["unet"], cfg, lat, img_lat, ehs, ati, STEPS, 1.0, 3.0, sds["cn"], cfg, cond_lat, 1.0)
     return VO.decode_latents(sds["vae"], lat, FRAMES, decode_chunk_size=8), lat
 

@@ -151,3 +151,17 @@ def test_vl_pipeline_end_to_end_without_text_vs_oracles(cpu_engines):
         ref = PC.run_vl_oracle(sds)
     want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert frames[0].shape == want.shape and rel_l2(frames[0], want) < 5e-2
+
+
+def test_vgl_pipeline_with_fp16_modules(cpu_engines):
+    """The reference casts every module to fp16 (weight_dtype, test_code/inference.py:357-368); the drop-ins keep the
+    caller's dtype at their boundaries and compute in bf16 / fp32 inside."""
+    mods, _ = PC.build("cpu")
+    for m in mods.values():
+        m.half()
+    sds = {k: {n: v.detach().float() for n, v in m.state_dict().items()} for k, m in mods.items()}
+    with torch.no_grad(), fake_lib.installed():
+        frames = PC.run_pipeline(mods, "cpu", output_type="pt")
+        ref, _ = PC.run_oracle(sds, latent_dtype=torch.float16)
+    want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert frames[0].dtype == torch.float32 and rel_l2(frames[0], want) < 5e-2

@@ -115,3 +115,26 @@ def test_encode_dedupes_identical_images(tiny):
     assert torch.equal(a[0], a[2]) and torch.equal(a[0], a[5]) and not torch.equal(a[0], a[1])
     assert rel_l2(a, b) < CAP and rel_l2(a[:, :4], VO.encode(sd, batch)) < CAP
     assert n_dedup * 2 == n_all  # 3 distinct images instead of 6
+
+
+def test_fp16_module_keeps_dtype_and_accuracy(monkeypatch):
+    """The reference runs its VAE in fp16 (test_code/inference.py:364): outputs come back in the caller's dtype."""
+    vae = build_vae(TINY_VAE).half()
+    sd = {k: v.float() for k, v in vae.state_dict().items()}
+    z, x = vae_inputs(4, 4, 6)
+    with torch.no_grad(), fake_lib.installed():
+        eng = VaeEngine(vae)
+        dec = eng.decode(z.half(), 2)
+        mom = eng.encode(x.half())
+    assert dec.dtype == torch.float16 and mom.dtype == torch.float16
+    assert rel_l2(dec, VO.decode(sd, z.half().float(), 2)) < CAP and rel_l2(mom[:, :4], VO.encode(sd, x.half().float())) < CAP
+
+
+def test_save_and_from_pretrained_round_trip(tmp_path):
+    from svd.autoencoder_kl_temporal_decoder import AutoencoderKLTemporalDecoder
+    vae = build_vae(TINY_VAE)
+    vae.save_pretrained(tmp_path / "vae")
+    again = AutoencoderKLTemporalDecoder.from_pretrained(str(tmp_path), subfolder="vae")
+    assert again.config.block_out_channels == (64, 128, 128, 128) and again.config.layers_per_block == 1
+    a, b = vae.state_dict(), again.state_dict()
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
