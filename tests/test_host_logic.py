@@ -99,3 +99,19 @@ def test_emulation_is_not_reachable_from_the_product():
     if not torch.cuda.is_available():
         with pytest.raises(lib.TtvdmError):
             lib.init()  # no CUDA device here: the product path fails loudly
+
+
+def test_emulation_covers_every_kernel_wrapper():
+    """A new entry point in lib.py must come with its emulation, or the host-logic tests silently stop covering it."""
+    import inspect
+    from this_and_that_vdm_b200 import lib
+    wrappers = {n for n, f in vars(lib).items()
+                if inspect.isfunction(f) and f.__module__ == lib.__name__ and not n.startswith("_")
+                and ("call(" in inspect.getsource(f) or "call_raw(" in inspect.getsource(f))
+                and n not in ("call", "call_raw")}
+    not_emulated = wrappers - set(fake_lib._PATCHED)
+    assert not_emulated == {"gesture_raster"}, not_emulated  # the rasteriser has its own oracle / golden tests
+    for n in set(fake_lib._PATCHED) & wrappers:
+        real = [p for p in inspect.signature(getattr(lib, n)).parameters]
+        fake = [p for p in inspect.signature(getattr(fake_lib, n)).parameters]
+        assert real == fake, (n, real, fake)
