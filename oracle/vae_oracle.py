@@ -27,7 +27,7 @@ Functional style over the diffusers-format state dict (keys `encoder.*`, `quant_
 """
 from __future__ import annotations
 
-from typing import Dict, Sequence
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

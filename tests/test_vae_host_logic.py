@@ -138,3 +138,24 @@ def test_save_and_from_pretrained_round_trip(tmp_path):
     assert again.config.block_out_channels == (64, 128, 128, 128) and again.config.layers_per_block == 1
     a, b = vae.state_dict(), again.state_dict()
     assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_decoder_mid_block_attention_is_scheduled_with_two_layers_per_block():
+    """layers_per_block = 2 (the SVD value): the decoder's mid block is ResBlock -> Attention -> ResBlock and every up
+    block has 3 ResBlocks; with layers_per_block = 1 the mid-block attention is never reached (diffusers zips
+    resnets[1:] with the attentions)."""
+    cfg = dict(block_out_channels=(64, 64, 128, 128), layers_per_block=2, down_block_types=("DownEncoderBlock2D",) * 4)
+    vae = build_vae(cfg, seed=99)
+    sd = state(vae)
+    z, x = vae_inputs(3, 4, 6, n_images=1)
+    with torch.no_grad(), fake_lib.installed():
+        eng = VaeEngine(vae)
+        assert len(eng.d_mid_res) == 2 and len(eng.d_mid_attn) == 1 and all(len(b["res"]) == 3 for b in eng.d_up)
+        dec = eng.decode(z, 3)
+        ref = VO.decode(sd, z, 3)
+        # knocking out the attention's output projection must change the result: the block is really on the path
+        sd2 = dict(sd)
+        sd2["decoder.mid_block.attentions.0.to_out.0.weight"] = torch.zeros_like(sd["decoder.mid_block.attentions.0.to_out.0.weight"])
+        assert rel_l2(VO.decode(sd2, z, 3), ref) > 1e-3
+        mom = eng.encode(x)
+    assert rel_l2(dec, ref) < CAP and rel_l2(mom[:, :4], VO.encode(sd, x)) < CAP

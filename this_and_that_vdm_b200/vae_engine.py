@@ -97,7 +97,7 @@ class VaeEngine:
         sd = dict(m.state_dict())
         g = lambda k: sd[k]  # noqa: E731
 
-        def res2d(p: str, r: Optional[VResW] = None) -> VResW:
+        def res2d(p: str) -> VResW:
             cout, cin = g(p + ".conv1.weight").shape[:2]
             r = VResW(cin=cin, cout=cout)
             r.n1_g, r.n1_b = _f32(g(p + ".norm1.weight"), dev), _f32(g(p + ".norm1.bias"), dev)
@@ -222,15 +222,15 @@ class VaeEngine:
                      bias=bias, res1=None if res1 is None else res1[sl], out_fp32=out_fp32)
         return out
 
-    def _linear(self, a, w, *, M, bias=None, res1=None, s0=1.0, out=None, out_fp32=False, ldo=None):
+    def _linear(self, a, w, *, M, bias=None, res1=None, out=None, out_fp32=False):
         N, K = w.shape
         if out is None:
             out = self._empty(M, N, dtype=torch.float32 if out_fp32 else BF16)
         rows_per = max(1, _MAX_ELEMS // max(N, K))
         for r0 in range(0, M, rows_per):
             r1 = min(M, r0 + rows_per)
-            lib.gemm(a[r0:r1], w, out[r0:r1], M=r1 - r0, N=N, k1=K, bias=bias, s0=s0,
-                     res1=None if res1 is None else res1[r0:r1], out_fp32=out_fp32, ldo=ldo)
+            lib.gemm(a[r0:r1], w, out[r0:r1], M=r1 - r0, N=N, k1=K, bias=bias,
+                     res1=None if res1 is None else res1[r0:r1], out_fp32=out_fp32)
         return out
 
     # ============================================================================================ blocks
