@@ -3,7 +3,7 @@
 PARITY PINNED (towers) / restated (assembly): `encode_clip` of the reference
 (svd/pipeline_stable_video_diffusion_controlnet.py:130-188; same code in svd/pipeline_stable_video_diffusion.py) calls
 two `transformers` modules — `self.image_encoder(image).image_embeds` (CLIPVisionModelWithProjection, loaded at
-test_code/inference.py:322-325) and `text_encoder(prompt)[0]` (CLIPTextModel, :347-348) — then concatenates
+test_code/inference.py:325-327) and `text_encoder(prompt)[0]` (CLIPTextModel, :347-348) — then concatenates
 [text(77) | image(1)] tokens, applies a freshly built `nn.LayerNorm((78, 1024))` (:172-173) and stacks zeros for
 classifier-free guidance (:176-186). `transformers` IS installed in this image (the reference pins 4.x, the image has
 5.5; the CLIP arithmetic is unchanged), so the tower restatements below are pinned against the library itself:

@@ -2,7 +2,7 @@
 (encode_clip, svd/pipeline_stable_video_diffusion_controlnet.py:130-188):
 
   * CLIPVisionModelWithProjection — `self.image_encoder(image).image_embeds` (:155); loaded by the reference at
-    test_code/inference.py:322-325 (`from_pretrained(path, subfolder="image_encoder", revision=None, variant="fp16")`)
+    test_code/inference.py:325-327 (`from_pretrained(path, subfolder="image_encoder", revision=None, variant="fp16")`)
   * CLIPTextModel — `text_encoder(prompt)[0]` (:166) with `prompt` = token ids [B, 77]; loaded at :347-348
 
 Same class names, `from_pretrained(path, subfolder=, variant=)` on the HF directory layout (`config.json` +
