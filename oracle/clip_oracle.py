@@ -103,7 +103,7 @@ def assemble(image_embeds: torch.Tensor, text_states: Optional[torch.Tensor], do
 
 
 def resize_with_antialiasing(image: torch.Tensor, size=(224, 224)) -> torch.Tensor:
-    """_resize_with_antialiasing of the reference (svd/pipeline_stable_video_diffusion_controlnet.py:733-760 region):
+    """_resize_with_antialiasing of the reference (svd/pipeline_stable_video_diffusion_controlnet.py:741-845):
     Gaussian pre-blur with sigma = max((factor - 1) / 2, 0.001), kernel 2*2*sigma (min 3, made odd), reflect padding,
     then bicubic interpolation with align_corners=True."""
     h, w = image.shape[-2:]
