@@ -280,7 +280,11 @@ def run_ours(args):
         achieved = gemm_alg / g["launches"] / (g["ms"] / g["launches"]) / 1e9  # TFLOP/s: alg flops per launch / avg ms
         roof = {"kernel": "gemm_kernel (linear + conv3x3 + temporal-conv family)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["bf16_tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "frac": round(achieved / peaks["bf16_tflops"], 4), "traffic": None,
+                "traffic_note": "family of 537 launches with different shapes: no single per-launch figure; ncu --set full of "
+                                "sampled launches shows DRAM bytes = algorithmic A + C bytes (profiles/r01b_ncu_full_gemm.csv: "
+                                "77-236 MB; profiles/r01c_vae_ncu_full.csv for the VAE shapes)",
+                "peak_source": peaks["source"],
                 "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
                 "algorithmic_tflop_per_step": round(gemm_alg / 1e12, 3),
                 "whole_step": {"algorithmic_tflop": round(step_flops(h, w, 2, True) / 1e12, 3),
