@@ -76,14 +76,20 @@ def _cond(n):
             "latents": torch.randn(n, 3, 4, 4, 4, generator=g) * 10}
 
 
-def _worker(rank, world, port, n_videos, out_path):
+def _fake_decode(state):
+    """Stands in for the VAE: [F, 4, h, w] -> [3, F, 2h, 2w]."""
+    up = state[:, :3].repeat_interleave(2, -1).repeat_interleave(2, -2) * 0.5 + 1.0
+    return up.permute(1, 0, 2, 3).contiguous()
+
+
+def _worker(rank, world, port, n_videos, out_path, with_decode=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from this_and_that_vdm_b200.sharding import run_sharded
     sig = torch.tensor([5.0, 3.0, 1.0, 0.0])
     ts = torch.tensor([0.4, 0.2, 0.0])
     res = run_sharded(n_videos, _cond(n_videos) if rank == 0 else None, torch.device("cpu"), FakeDenoiser, sig, ts,
-                      torch.linspace(1, 3, 3), vgl=True)
+                      torch.linspace(1, 3, 3), vgl=True, decode=_fake_decode if with_decode else None)
     if rank == 0:
         torch.save(res, out_path)
     else:
@@ -122,3 +128,15 @@ def test_sharded_equals_single_rank(tmp_path, n_videos):
             d.euler_update(i, st, e[:48], e[48:])
         ref.append(st)
     assert torch.equal(got, torch.stack(ref))
+
+
+@pytest.mark.parametrize("n_videos", [1, 3])
+def test_sharded_decode_on_every_rank(tmp_path, n_videos):
+    """With `decode=` each rank decodes the videos it finished and the one gather carries the decoded videos: N = 1 on 2
+    ranks is a split pair (the cond-half rank decodes nothing and must still join the gather with the right shape)."""
+    lat_path, dec_path = tmp_path / "lat.pt", tmp_path / "dec.pt"
+    mp.spawn(_worker, args=(2, _free_port(), n_videos, str(lat_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_videos, str(dec_path), True), nprocs=2, join=True)
+    lat, dec = torch.load(lat_path), torch.load(dec_path)
+    assert dec.shape == (n_videos, 3, 3, 8, 8)
+    assert torch.equal(dec, torch.stack([_fake_decode(x) for x in lat]))

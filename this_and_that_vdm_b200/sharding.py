@@ -118,12 +118,18 @@ def exchange_eps(eps_local: torch.Tensor, my_offset: int, partner: int) -> Tuple
 def run_sharded(n_videos: int, cond: Optional[Dict[str, torch.Tensor]], device,
                 make_denoiser: Callable[[], "object"], sigmas: torch.Tensor, timesteps: torch.Tensor,
                 guidance: torch.Tensor, *, vgl: bool = True, conditioning_scale: float = 1.0,
-                max_steps: Optional[int] = None) -> Optional[torch.Tensor]:
+                max_steps: Optional[int] = None,
+                decode: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> Optional[torch.Tensor]:
     """Denoises `n_videos` videos across the ranks of the default process group.
 
     `cond` (rank 0 only): encoder_hidden_states [2N, L, D] (uncond rows first), image_latents [2N, 4, h, w],
     added_time_ids [2N, 3], controlnet_cond [N, F, 4, h, w] (VGL), latents [N, F, 4, h, w] (x init_noise_sigma).
-    Returns on rank 0 the final latents [N, F, 4, h, w]; None elsewhere."""
+    Returns on rank 0 the final latents [N, F, 4, h, w]; None elsewhere.
+
+    `decode` (optional): latents [F, 4, h, w] -> decoded video (any fixed shape, e.g. the VAE engine's
+    `decode_latents` giving [3, F, H, W]). Every rank then decodes the videos it finished (the uncond-half rank of a
+    split pair; its partner contributes zeros) and the ONE gather carries the decoded videos instead of the latents,
+    so the VAE work is spread over the ranks as well; rank 0 gets [N, *decoded shape]."""
     rank, world = dist.get_rank(), dist.get_world_size()
     c = broadcast_conditioning(cond, device)
     N = n_videos
@@ -133,6 +139,7 @@ def run_sharded(n_videos: int, cond: Optional[Dict[str, torch.Tensor]], device,
     den = make_denoiser()
     results = torch.zeros(max(n_slots, 1), Fr, 4, h, w, dtype=torch.float32, device=device)
     n_steps = len(timesteps) if max_steps is None else min(max_steps, len(timesteps))
+    decoded: Optional[torch.Tensor] = None
     for slot, a in enumerate(mine):
         idx = [a.video, N + a.video]
         state = c["latents"][a.video].clone().contiguous()
@@ -148,11 +155,25 @@ def run_sharded(n_videos: int, cond: Optional[Dict[str, torch.Tensor]], device,
             else:
                 eu, ec = exchange_eps(eps, a.batch_offset, a.partner)
             den.euler_update(i, state, eu, ec)
-        results[slot] = state
+        if decode is None:
+            results[slot] = state
+        elif a.batch_offset == 0:
+            frames = decode(state).to(torch.float32)
+            if decoded is None:
+                decoded = torch.zeros(max(n_slots, 1), *frames.shape, dtype=torch.float32, device=device)
+            decoded[slot] = frames
+    if decode is not None:
+        # ranks that decoded nothing (idle, or only cond halves) learn the decoded shape before the gather
+        dims = list(decoded.shape[1:]) if decoded is not None else []
+        shape = torch.tensor(dims + [0] * (8 - len(dims)), dtype=torch.int64, device=device)
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+        full = tuple(int(v) for v in shape.tolist() if v > 0)
+        results = decoded if decoded is not None else torch.zeros(max(n_slots, 1), *full, dtype=torch.float32,
+                                                                  device=device)
     outs = gather_latents(results)
     if rank != 0:
         return None
-    final = torch.zeros(N, Fr, 4, h, w, dtype=torch.float32, device=device)
+    final = torch.zeros(N, *results.shape[1:], dtype=torch.float32, device=device)
     pl = plan(N, world)
     for r in range(world):
         for slot, a in enumerate(pl[r]):
