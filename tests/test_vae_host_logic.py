@@ -159,3 +159,35 @@ def test_decoder_mid_block_attention_is_scheduled_with_two_layers_per_block():
         assert rel_l2(VO.decode(sd2, z, 3), ref) > 1e-3
         mom = eng.encode(x)
     assert rel_l2(dec, ref) < CAP and rel_l2(mom[:, :4], VO.encode(sd, x)) < CAP
+
+
+def test_flop_census_matches_the_schedule(tiny):
+    """tools/flop_census.vae_{de,en}code_flops (the algorithmic figure DESIGN.md quotes) against the FLOPs of the GEMM
+    calls the engine really makes (the engine pads conv_in to 64 input channels, conv_out to 4 / 8 outputs and the
+    attention's key dimension to a multiple of 64, so it may only be slightly ABOVE the census)."""
+    from tools.flop_census import vae_decode_flops, vae_encode_flops
+    vae, eng, sd = tiny
+    counted = []
+    real_gemm = fake_lib.gemm
+
+    def counting_gemm(a, w, out, **kw):
+        taps = {0: 1, 1: 9, 2: 3}[kw.get("mode", 0)]
+        counted.append(2.0 * kw["M"] * kw["N"] * taps * (kw["k1"] + kw.get("k2", 0)))
+        return real_gemm(a, w, out, **kw)
+
+    z, x = vae_inputs(4, 8, 8, n_images=2)
+    kw = dict(chans=(64, 128, 128, 128), layers_per_block=1)
+    with torch.no_grad(), fake_lib.installed():
+        from this_and_that_vdm_b200 import lib
+        lib.gemm = counting_gemm
+        eng.decode(z, 4)
+        dec = sum(counted)
+        counted.clear()
+        eng.encode(x, dedupe=False)
+        enc = sum(counted)
+    a_dec, a_enc = vae_decode_flops(8, 8, 4, **kw), vae_encode_flops(64, 64, 2, **kw)
+    assert a_dec <= dec <= 1.06 * a_dec, (dec, a_dec)
+    pad_in = 2 * 2.0 * 64 * 64 * 9 * (64 - 3) * 64  # the 3 input channels travel as one 64-wide K chunk (2 images)
+    assert a_enc <= enc <= 1.02 * a_enc + pad_in, (enc, a_enc, pad_in)
+    # the published size: 14 x 576 x 1024
+    assert abs(vae_decode_flops(72, 128, 14) / 1e12 - 97.3) < 1.5

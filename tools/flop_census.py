@@ -157,3 +157,54 @@ if __name__ == "__main__":
         fu, _ = census(72, 128, 2)
         for k, v in sorted(fu.items(), key=lambda kv: -kv[1]):
             print(f"   {k:22s} {v / 1e12:9.4f} TF")
+
+
+# ---------------------------------------------------------------------------------------------- VAE
+def vae_decode_flops(h: int, w: int, frames: int, chans=(128, 256, 512, 512), layers_per_block: int = 2) -> float:
+    """Algorithmic FLOPs (2 x MACs; norms / activations = 0) of AutoencoderKLTemporalDecoder.decode for `frames` latent
+    frames of h x w: conv_in, mid block (SpatioTemporalResBlock, 1-head attention, SpatioTemporalResBlock), 4 up blocks
+    of (layers_per_block + 1) SpatioTemporalResBlocks + nearest x2 conv, conv_out 128->3, time_conv_out."""
+    def st_res(s, cin, cout):
+        f = 2.0 * s * 9 * (cin * cout + cout * cout)          # spatial conv1 + conv2
+        if cin != cout:
+            f += 2.0 * s * cin * cout                          # 1x1 shortcut
+        return f + 2.0 * s * 3 * cout * cout * 2               # two (3,1,1) temporal convs
+
+    s = h * w
+    top = chans[-1]
+    f = 2.0 * s * 9 * 4 * top                                  # conv_in
+    f += st_res(s, top, top)
+    for _ in range(layers_per_block - 1):
+        f += 4 * 2.0 * s * top * top + 4.0 * s * s * top       # q, k, v, out linears + QK^T + PV (one head)
+        f += st_res(s, top, top)
+    rev = list(reversed(chans))
+    c = rev[0]
+    for i, co in enumerate(rev):
+        for j in range(layers_per_block + 1):
+            f += st_res(s, c if j == 0 else co, co)
+        c = co
+        if i != len(rev) - 1:
+            s *= 4
+            f += 2.0 * s * 9 * co * co                         # Upsample2D conv
+    f += 2.0 * s * 9 * chans[0] * 3 + 2.0 * s * 3 * 3 * 3      # conv_out + time_conv_out
+    return f * frames
+
+
+def vae_encode_flops(H: int, W: int, images: int, chans=(128, 256, 512, 512), layers_per_block: int = 2) -> float:
+    """Same for AutoencoderKLTemporalDecoder.encode of `images` H x W images (quant_conv folded into conv_out)."""
+    def res(s, cin, cout):
+        return 2.0 * s * 9 * (cin * cout + cout * cout) + (2.0 * s * cin * cout if cin != cout else 0.0)
+
+    s = H * W
+    f = 2.0 * s * 9 * 3 * chans[0]
+    c = chans[0]
+    for i, co in enumerate(chans):
+        for j in range(layers_per_block):
+            f += res(s, c if j == 0 else co, co)
+        c = co
+        if i != len(chans) - 1:
+            s //= 4
+            f += 2.0 * s * 9 * co * co                         # stride-2 conv
+    f += 2 * res(s, c, c) + 4 * 2.0 * s * c * c + 4.0 * s * s * c
+    f += 2.0 * s * 9 * c * 8 + 2.0 * s * 8 * 8                 # conv_out 512 -> 8, quant_conv 8 -> 8
+    return f * images
