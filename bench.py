@@ -32,6 +32,9 @@ sys.path.insert(0, str(ROOT))
 
 FRAMES = 14
 NUM_STEPS = 25
+# The CPU baseline always uses the same number of host threads (BENCH and SCALE boxes expose different core counts; a
+# fixed figure keeps the driver's value / reference ratio comparable between the two files).
+CPU_BASELINE_THREADS = min(16, os.cpu_count() or 1)
 
 
 def load_peaks():
@@ -231,7 +234,7 @@ def run_ours(args):
 
     one_video_e2e()  # warm
     sync()
-    n_e2e = max(1, min(args.steps, 2))
+    n_e2e = max(5, min(args.steps, 8)) if not args.quick_e2e else 1
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         one_video_e2e()
@@ -300,6 +303,12 @@ def run_ours(args):
             full = full_pipeline_extra(args, dev, unet, cn)
         except Exception as e:  # noqa: BLE001  (an extra must never cost the bench line)
             full = {"error": f"{type(e).__name__}: {e}"[:300]}
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        try:
+            eager = eager_bf16_gpu(dev, unet, cn, sizes=((32, 48), (h, w)) if (h, w) != (32, 48) else ((32, 48),))
+        except Exception as e:  # noqa: BLE001
+            eager = {"error": f"{type(e).__name__}: {e}"[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference(args, sample_only=True)
@@ -321,6 +330,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_shares": shares,
             "gemm_shapes": gemm_shapes if rank == 0 else None,
             "cpu_baseline": cpu,
+            "eager_bf16_gpu": eager,
             "full_pipeline": full,
         }
         print(json.dumps(line), flush=True)
@@ -379,6 +389,63 @@ def full_pipeline_extra(args, dev, unet, cn):
             "note": "extra; the headline metric and `e2e` cover the denoising loop only (latent mode)"}
 
 
+# ====================================================================================================== eager bf16 on the same GPU
+def eager_bf16_gpu(dev, unet, cn, sizes=((32, 48), (72, 128)), warm=2, iters=3):
+    """The competitor the reference actually runs on a GPU (SURVEY.md §8d last bullet): its torch-eager
+    path — cuDNN convolutions, cuBLAS linears, F.scaled_dot_product_attention — in bf16 on the SAME B200. diffusers is
+    not installable, so the graph is the oracle's restatement of it (pinned to the reference's own forward code by
+    tests/test_reference_pin.py) moved to CUDA bf16: one VGL Euler step (GestureNet + UNet, CFG pair, all the
+    reference's per-step recomputation included). A reported baseline; nothing of it is on the product path."""
+    from oracle import svd_oracle as O
+    torch.backends.cudnn.benchmark = True
+    usd = {k: v.detach().to(dev, torch.bfloat16) for k, v in unet.state_dict().items()}
+    csd = {k: v.detach().to(dev, torch.bfloat16) for k, v in cn.state_dict().items()}
+    cfg = dict(O.SVD_CONFIG)
+    sig = O.karras_sigmas(NUM_STEPS)
+    ts = O.euler_timesteps(sig).to(dev)
+    out = {}
+    for (h, w) in sizes:
+        c = synth_inputs(h, w, 1, seed=0)
+        lat = c["latents"].to(dev)
+        img = c["image_latents"][:, None].repeat(1, FRAMES, 1, 1, 1).to(dev, torch.bfloat16)
+        ehs = c["encoder_hidden_states"].to(dev, torch.bfloat16)
+        ati = c["added_time_ids"].to(dev, torch.bfloat16)
+        cc = torch.cat([c["controlnet_cond"][0]] * 2).to(dev, torch.bfloat16)
+        gd = torch.linspace(1.0, 3.0, FRAMES, device=dev)[None, :, None, None, None]
+
+        def step(i):
+            s, sn = float(sig[i]), float(sig[i + 1])
+            x = (torch.cat([lat] * 2) / (s * s + 1) ** 0.5).to(torch.bfloat16)
+            x = torch.cat([x, img], dim=2)
+            d, m = O.controlnet_forward(csd, cfg, x, ts[i], ehs, ati, cc, 1.0)
+            eps = O.unet_forward(usd, cfg, x, ts[i], ehs, ati, d, m).float()
+            eu, ec = eps.chunk(2)
+            return O.euler_step(eu + gd * (ec - eu), lat, s, sn)
+
+        try:
+            with torch.no_grad():
+                for i in range(warm):
+                    step(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(iters):
+                    step(warm + i)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[f"{h * 8}x{w * 8}"] = {"ms_per_euler_step": round(ms, 2),
+                                       "frames_per_s_25_steps": round(FRAMES / (NUM_STEPS * ms / 1e3), 4)}
+        except Exception as e:  # noqa: BLE001
+            out[f"{h * 8}x{w * 8}"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = ("torch-eager bf16 (cuDNN / cuBLAS / SDPA, cudnn.benchmark on) of the reference graph as restated by the "
+                   "oracle, one VGL Euler step, CUDA events, same GPU and process as `value`")
+    del usd, csd
+    torch.cuda.empty_cache()
+    return out
+
+
 # ====================================================================================================== reference arm
 def cpu_reference(args, sample_only: bool = False, steps: int = 1, warmup: int = 0):
     """The reference's CPU path = the fp32 oracle on all host threads. Bounded sample: ONE VGL Euler step (GestureNet +
@@ -386,7 +453,7 @@ def cpu_reference(args, sample_only: bool = False, steps: int = 1, warmup: int =
     workload by the algorithmic FLOP ratio (tools/flop_census.py)."""
     from oracle import svd_oracle as O
     from tools.flop_census import step_flops
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(CPU_BASELINE_THREADS)
     h, w = args.height // 8, args.width // 8
     sh, sw = min(h, 32), min(w, 48)
     unet, cn = build_models("cpu")
@@ -442,6 +509,8 @@ def main():
     ap.add_argument("--height", type=int, default=576)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager bf16 leg (same GPU, N = 1 only)")
+    ap.add_argument("--quick-e2e", action="store_true", help="time 1 e2e video instead of >= 5 (development runs)")
     ap.add_argument("--no-full-pipeline", action="store_true", help="skip the image -> frames extra (N = 1 only)")
     ap.add_argument("--profile-only", action="store_true", help="run prepare + 2 Euler steps; cudaProfilerStart/Stop around the 2nd")
     args = ap.parse_args()

@@ -35,6 +35,8 @@ typedef enum {
 
 /* Process-wide immutable state (driver entry points, SM count). Safe to call repeatedly. */
 int ttvdm_init(int device);
+/* Drops that state again (the library owns no device memory, streams or events); a later call re-initialises. */
+int ttvdm_destroy(void);
 /* Copies the last error message of the calling thread into buf (NUL terminated). */
 int ttvdm_last_error(char* buf, size_t n);
 /* Library / ABI version, bumped when a struct below changes. */
@@ -84,6 +86,34 @@ typedef struct {
   int geglu;
   void* out; int ldo; int out_fp32;     /* bf16 (default) or fp32 output, row stride ldo elements */
   int act;                              /* 0 none, 1 SiLU (TimestepEmbedding MLPs) */
+  /* ---- normalisation fusions (ABI 3). All optional (NULL = off); bf16 output, N % 64 == 0, no GEGLU for the *_out ones.
+   * gn_stats_out : double [M / gn_rows_per_inst][N / 2][2] — the epilogue ADDS, per group instance and channel PAIR, the
+   *                sum and sum of squares of the bf16 values it stores (caller zeroes the buffer). Sums are kept in
+   *                shared memory per CTA — which then walks a CONTIGUOUS range of tiles — and reach the buffer as a
+   *                few fp64 atomics per CTA and instance, not per tile. The
+   *                GroupNorm that consumes `out` (ttvdm_groupnorm.pstats1/2) then needs no statistics pass: north-star
+   *                "GroupNorm fused into the preceding conv's epilogue" (diffusers ResnetBlock2D / TemporalResnetBlock
+   *                norm1/norm2 via svd/diffusion_arch/unet_3d_blocks.py:1891-2311, TransformerSpatioTemporalModel.norm
+   *                svd/diffusion_arch/transformer_temporal.py:234,323, conv_norm_out svd/unet_spatio_temporal_condition.py:244).
+   * row_sums_out : float [N / 32][M][2] — per row and 32-column chunk, sum / sum of squares of the bf16 values stored
+   *                (plain stores, exactly one writer per slot: no zeroing, no atomics, bit-reproducible): the LayerNorm
+   *                statistics of the consumer (BasicTransformerBlock / TemporalBasicTransformerBlock norm1-3, norm_in).
+   * ln_rowsums   : float [K / 32][M][2] of the A operand (the producer's row_sums_out; K = k1 + k2). When set, A is the UN-normalised
+   *                tensor, W must have the LayerNorm gain folded in (W' = W diag(gamma)), `bias` the folded bias
+   *                (b + W beta), ln_colsum[n] = sum_k W'[n, k], and the epilogue computes
+   *                    LN(A) W^T + b  =  rstd_r * (acc_rn + prevec[(r / prevec_rows) % prevec_mod][n] - mean_r * ln_colsum[n]) + bias[n]
+   *                so the LayerNorm kernel and its round trip through HBM disappear. ln_sum_add / ln_sq_add (per prevec
+   *                row: [prevec_mod][2] floats or NULL) are added to the row sums first (frame positional embedding,
+   *                svd/diffusion_arch/transformer_temporal.py:356).
+   */
+  void* gn_stats_out; int gn_rows_per_inst;
+  float* row_sums_out;
+  /* row sums are taken over  stored_bf16(out)[r, n] + rs_addvec[(r / rs_add_rows) % rs_add_mod][n]  (fp32 [rs_add_mod, ld_rs_add]
+   * or NULL): the consumer normalises `out + frame positional embedding` without that sum ever being materialised */
+  const float* rs_addvec; int rs_add_rows; int rs_add_mod; int ld_rs_add;
+  const float* ln_rowsums; const float* ln_colsum; float ln_eps;
+  const float* prevec; int prevec_rows; int prevec_mod; int ldpv;
+  const float* ln_row_add;              /* [prevec_mod][2] or NULL */
 } ttvdm_gemm_params;
 
 int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream);
@@ -156,6 +186,10 @@ typedef struct {
   const float* gamma; const float* beta; /* [c1+c2] */
   int silu;
   void* out; int ldo;        /* bf16 [rows, c1+c2] */
+  /* ABI 3: per-(instance, channel pair) sums produced by the epilogue of the GEMM that wrote x1 / x2
+   * (ttvdm_gemm_params.gn_stats_out, same rows_per_inst): double [n_inst][c/2][2] or NULL. A source with pstats is not
+   * read by the statistics pass; with all sources covered that pass is not launched at all. */
+  const void* pstats1; const void* pstats2;
 } ttvdm_groupnorm_params;
 int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream);
 
@@ -275,6 +309,45 @@ int ttvdm_vae_time_conv_out(const float* x, int ldx, const float* w, const float
  * ------------------------------------------------------------------------------------------------ */
 int ttvdm_act_inplace(void* x, size_t n, int kind, void* stream);
 int ttvdm_layernorm_flat(const float* x, float* out, int rows, size_t n, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight repack entry points (run once per model load). Sources are PyTorch-layout parameters exactly as a
+ * diffusers state dict holds them (svd/unet_spatio_temporal_condition.py / svd/temporal_controlnet.py modules), in fp32,
+ * fp16 or bf16; outputs are the operands ttvdm_gemm consumes.
+ *  pack_conv_weight : w [cout, cin, taps] (Conv2d 3x3: taps = 9 row-major (ky, kx); Conv3d (3,1,1): taps = 3; 1x1: taps = 1)
+ *                     -> out bf16 [cout, taps * cin_pad], tap-major then channel, channels zero-padded to cin_pad.
+ *  pack_linear      : w [N, K] (+ bias [N]) with an optional LayerNorm(gamma, beta) folded in front of it:
+ *                        out_w[row, k]   = bf16(w[n, k] * gamma[k])
+ *                        out_colsum[row] = sum_k out_w[row, k]                       (fp32; NULL to skip)
+ *                        out_bias[row]   = bias[n] + sum_k w[n, k] * beta[k]         (fp32; NULL to skip)
+ *                     row = out_row0 + n, or with geglu = 1 the (hidden_j, gate_j) interleave the GEGLU epilogue expects
+ *                     (row = out_row0 + 2n for n < N/2, out_row0 + 2(n - N/2) + 1 otherwise). ldo = row stride of out_w.
+ *                     out_row0 lets to_q | to_k | to_v land in one fused [3C, C] operand.
+ *  pack_vector      : cast n elements to fp32 (biases, norm affine parameters).
+ * ------------------------------------------------------------------------------------------------ */
+enum { TTVDM_DT_F32 = 0, TTVDM_DT_F16 = 1, TTVDM_DT_BF16 = 2 };
+int ttvdm_pack_conv_weight(const void* w, int src_dtype, int cout, int cin, int taps, int cin_pad, void* out, void* stream);
+typedef struct {
+  const void* w; const void* bias;          /* [N, K], [N] or NULL */
+  const void* gamma; const void* beta;      /* [K] or NULL: LayerNorm in front of the linear */
+  int src_dtype;                            /* TTVDM_DT_* of w / bias / gamma / beta */
+  int N, K;
+  int geglu; int out_row0; int ldo;
+  void* out_w; float* out_bias; float* out_colsum;
+} ttvdm_pack_linear_params;
+int ttvdm_pack_linear(const ttvdm_pack_linear_params* p, void* stream);
+int ttvdm_pack_vector(const void* src, int src_dtype, size_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Workspace queries. No entry point allocates; the only caller-provided scratch areas are the ones below (all others
+ * need none, which the two *_workspace_bytes queries state explicitly).
+ * ------------------------------------------------------------------------------------------------ */
+size_t ttvdm_groupnorm_workspace_bytes(int rows, int rows_per_inst);      /* ttvdm_groupnorm_params.stats */
+size_t ttvdm_gemm_gn_stats_bytes(int M, int N, int gn_rows_per_inst);     /* ttvdm_gemm_params.gn_stats_out */
+size_t ttvdm_gemm_row_sums_bytes(int M, int N);                           /* ttvdm_gemm_params.row_sums_out */
+size_t ttvdm_gemm_workspace_bytes(const ttvdm_gemm_params* p);            /* 0 */
+size_t ttvdm_attn_workspace_bytes(const ttvdm_attn_params* p);            /* 0 */
+size_t ttvdm_gesture_scratch_bytes(int n_points, int H, int W);           /* ttvdm_gesture_params.scratch */
 
 #ifdef __cplusplus
 }

@@ -145,9 +145,22 @@ class SVDPipelineBase:
         return torch.from_numpy(arr.transpose(0, 3, 1, 2))
 
     def _preprocess_image(self, image, height, width) -> torch.Tensor:
-        """VaeImageProcessor.preprocess: resize to (height, width), map [0,1] -> [-1,1]."""
+        """diffusers VaeImageProcessor.preprocess(image, height, width) as the reference calls it
+        (svd/pipeline_stable_video_diffusion_controlnet.py:541): PIL images are converted to RGB, Lanczos-resized and
+        mapped [0,1] -> [-1,1]; tensors (or lists of tensors) are concatenated / stacked, returned untouched when they
+        are 4-channel latents, otherwise resized with F.interpolate (nearest) and mapped [0,1] -> [-1,1] unless they
+        already contain negative values (diffusers warns and skips the normalisation in that case)."""
         if isinstance(image, torch.Tensor):
-            return image
+            image = [image]
+        if isinstance(image, list) and len(image) > 0 and isinstance(image[0], torch.Tensor):
+            t = torch.cat(image, dim=0) if image[0].ndim == 4 else torch.stack(image, dim=0)
+            if t.shape[1] == 4:
+                return t
+            if tuple(t.shape[-2:]) != (height, width):
+                t = torch.nn.functional.interpolate(t, size=(height, width))
+            if t.min() < 0:
+                return t
+            return 2.0 * t - 1.0
         imgs = image if isinstance(image, list) else [image]
         imgs = [i.convert("RGB").resize((width, height), resample=PIL.Image.LANCZOS) for i in imgs]
         return 2.0 * self._pil_to_pt(imgs) - 1.0

@@ -37,7 +37,9 @@ def _count(n: int = 1) -> None:
 
 def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda2=0, n_img=0, H=0, W=0, bias=None,
          rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None, ldr1=0, s1=1.0, res2=None, ldr2=0, s2=1.0,
-         geglu=False, ldo=None, out_fp32=False, act=0) -> None:
+         geglu=False, ldo=None, out_fp32=False, act=0, gn_stats_out=None, gn_rows_per_inst=0, row_sums_out=None, rs_addvec=None, rs_add_rows=0, rs_add_mod=0,
+         ln_rowsums=None, ln_colsum=None, ln_eps=1e-5, prevec=None, prevec_rows=0, prevec_mod=0, ldpv=0,
+         ln_row_add=None) -> None:
     assert k1 % 64 == 0 and k2 % 64 == 0, "gemm: k1 / k2 must be multiples of 64"
     assert a.dtype == BF16 and w.dtype == BF16
     lda = k1 if lda is None else lda
@@ -58,6 +60,21 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
         x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1)
         xp = Fn.pad(x, (0, 0, 0, 0, 1, 1))
         acc = sum(xp[:, t:t + H] @ wm[:, t * k1:(t + 1) * k1].t() for t in range(3)).reshape(M, N)
+    if ln_rowsums is not None:
+        # LayerNorm of A folded into the epilogue: rstd * (acc + prevec - mean * colsum)  (include/ttvdm.h, ABI 3)
+        assert ln_colsum is not None and N % 32 == 0 and not out_fp32
+        parts = (k1 + k2) // 32
+        rs = ln_rowsums.view(-1)[: parts * M * 2].view(parts, M, 2).float().sum(0)
+        if prevec_mod > 0:
+            pidx = (torch.arange(M) // prevec_rows) % prevec_mod
+            if ln_row_add is not None:
+                rs = rs + _mat(ln_row_add, prevec_mod, 2, 2).float()[pidx]
+            if prevec is not None:
+                acc = acc + _mat(prevec, prevec_mod, N, ldpv if ldpv else N).float()[pidx]
+        mean = rs[:, 0] / (k1 + k2)
+        var = (rs[:, 1] / (k1 + k2) - mean * mean).clamp_min(0)
+        rstd = torch.rsqrt(var + ln_eps)
+        acc = rstd[:, None] * (acc - mean[:, None] * ln_colsum.float()[None, :N])
     if bias is not None:
         acc = acc + bias.float()[:N]
     if rowvec is not None:
@@ -83,6 +100,23 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
     ldo = ldo if ldo is not None else n_out
     assert out.dtype == (torch.float32 if out_fp32 else BF16)
     _mat(out, M, n_out, ldo).copy_(val.to(out.dtype))
+    if gn_stats_out is not None or row_sums_out is not None:
+        assert not geglu and not out_fp32 and N % 32 == 0
+        stored = val.to(BF16).double()  # statistics of exactly what was stored
+        if gn_stats_out is not None:
+            assert gn_stats_out.dtype == torch.float64 and gn_rows_per_inst > 0 and M % gn_rows_per_inst == 0
+            n_inst = M // gn_rows_per_inst
+            v = stored.view(n_inst, gn_rows_per_inst, N // 2, 2)
+            st = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)  # [n_inst, N/2, 2]
+            gn_stats_out.view(-1)[: n_inst * N].add_(st.reshape(-1))
+        if row_sums_out is not None:
+            assert row_sums_out.dtype == torch.float32
+            if rs_addvec is not None:
+                idx = (torch.arange(M) // rs_add_rows) % rs_add_mod
+                stored = stored + _mat(rs_addvec, rs_add_mod, N, N).double()[idx]
+            ch = stored.view(M, N // 32, 32)
+            part = torch.stack([ch.sum(-1), (ch * ch).sum(-1)], -1).permute(1, 0, 2)  # [N/32, M, 2]
+            row_sums_out.view(-1)[: (N // 32) * M * 2].copy_(part.float().reshape(-1))
     _count()
 
 
@@ -126,20 +160,38 @@ def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) ->
 
 
 def groupnorm(x1, out, stats, gamma, beta, *, c1, rows, rows_per_inst, eps, silu, x2=None, c2=0, ld1=None, ld2=None,
-              ldo=None) -> None:
+              ldo=None, pstats1=None, pstats2=None) -> None:
     assert (c1 + c2) % 32 == 0 and c1 % 8 == 0 and c2 % 8 == 0 and rows % rows_per_inst == 0
-    assert stats.dtype == torch.float64 and stats.numel() >= (rows // rows_per_inst) * 64
+    need_pass = pstats1 is None or (x2 is not None and pstats2 is None)
+    if need_pass:
+        assert stats.dtype == torch.float64 and stats.numel() >= (rows // rows_per_inst) * 64
     x = _mat(x1, rows, c1, c1 if ld1 is None else ld1).float()
     if x2 is not None:
         x = torch.cat([x, _mat(x2, rows, c2, c2 if ld2 is None else ld2).float()], 1)
     C = c1 + c2
     n_inst = rows // rows_per_inst
-    xi = x.view(n_inst, rows_per_inst, C).permute(0, 2, 1)  # [inst, C, rows] == N, C, *
-    y = Fn.group_norm(xi, 32, gamma.float(), beta.float(), eps).permute(0, 2, 1).reshape(rows, C)
+    cpg = C // 32
+    # group sums: from the tensor itself for sources without producer statistics, from the per-pair sums otherwise
+    xi = x.double().view(n_inst, rows_per_inst, C)
+    ch_s, ch_q = xi.sum(1), (xi * xi).sum(1)  # [n_inst, C]
+    for ps, off, c in ((pstats1, 0, c1), (pstats2 if x2 is not None else None, c1, c2)):
+        if ps is not None:
+            assert cpg % 2 == 0 and ps.dtype == torch.float64
+            pv = ps.view(-1)[: n_inst * c].view(n_inst, c // 2, 2)
+            # spread each pair's sums over its two channels (only the group totals matter)
+            ch_s[:, off:off + c] = (pv[:, :, 0] / 2).repeat_interleave(2, 1)
+            ch_q[:, off:off + c] = (pv[:, :, 1] / 2).repeat_interleave(2, 1)
+    n = rows_per_inst * cpg
+    mean = ch_s.view(n_inst, 32, cpg).sum(-1) / n
+    var = (ch_q.view(n_inst, 32, cpg).sum(-1) / n - mean * mean).clamp_min(0)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    mean_c = mean.float().repeat_interleave(cpg, 1)[:, None, :]
+    rstd_c = rstd.float().repeat_interleave(cpg, 1)[:, None, :]
+    y = ((x.view(n_inst, rows_per_inst, C) - mean_c) * rstd_c * gamma.float() + beta.float()).reshape(rows, C)
     if silu:
         y = Fn.silu(y)
     _mat(out, rows, C, C if ldo is None else ldo).copy_(y.to(BF16))
-    _count(3)  # memset + stats + apply
+    _count(3 if need_pass else 1)  # memset + stats + apply / apply only
 
 
 def layernorm(x, out, gamma, beta, *, rows, C, eps=1e-5, addvec=None, F=0, S=0, sum_out=None, ldx=None, ldo=None,
@@ -251,13 +303,52 @@ def layernorm_flat(x, out, *, rows, n, eps=1e-5) -> None:
     _count()
 
 
+# ---- weight repack entry points
+def pack_conv_weight(w, out, *, cin_pad=0) -> None:
+    cout, cin = w.shape[:2]
+    taps = w[0, 0].numel()
+    cp = max(cin_pad, cin)
+    v = w.detach().float().reshape(cout, cin, taps).permute(0, 2, 1)  # [cout, taps, cin]
+    if cp > cin:
+        v = Fn.pad(v, (0, cp - cin))
+    out.view(-1)[: cout * taps * cp].copy_(v.reshape(-1).to(BF16))
+    _count()
+
+
+def pack_linear(w, out_w, *, bias=None, gamma=None, beta=None, out_bias=None, out_colsum=None, geglu=False,
+                out_row0=0) -> None:
+    N = w.shape[0]
+    w32 = w.detach().float().reshape(N, -1)
+    wf = (w32 * gamma.detach().float()[None, :] if gamma is not None else w32).to(BF16)
+    rows = torch.arange(N)
+    if geglu:
+        half = N // 2
+        rows = torch.where(rows < half, 2 * rows, 2 * (rows - half) + 1)
+    rows = rows + out_row0
+    out_w[rows] = wf
+    if out_colsum is not None:
+        out_colsum[rows] = wf.float().sum(1)
+    if out_bias is not None:
+        b = w32 @ beta.detach().float() if beta is not None else torch.zeros(N)
+        if bias is not None:
+            b = b + bias.detach().float()
+        out_bias[rows] = b
+    _count()
+
+
+def pack_vector(src, out) -> None:
+    out.view(-1)[: src.numel()].copy_(src.detach().float().reshape(-1))
+    _count()
+
+
 def launch_count() -> int:
     return _launches
 
 
 _PATCHED = ["gemm", "attn_spatial", "attn_cross", "attn_temporal", "groupnorm", "layernorm", "im2col_s2", "upsample2x",
             "sinusoid", "axpy", "sampler_prepare", "sampler_euler_step", "softmax_rows", "im2col_s2_pad01",
-            "vae_time_conv_out", "act_inplace", "layernorm_flat", "launch_count"]
+            "vae_time_conv_out", "act_inplace", "layernorm_flat", "launch_count", "pack_conv_weight", "pack_linear",
+            "pack_vector"]
 
 
 @contextlib.contextmanager

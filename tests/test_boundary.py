@@ -20,12 +20,12 @@ def _header():
 def test_library_exports_every_declared_symbol():
     from this_and_that_vdm_b200 import lib
     l = lib.load()
-    declared = set(re.findall(r"^\s*(?:int|uint64_t)\s+(ttvdm_\w+)\s*\(", _header(), flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|uint64_t|size_t)\s+(ttvdm_\w+)\s*\(", _header(), flags=re.M))
     assert declared, "no declarations parsed"
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for name in declared:
         assert hasattr(l, name), name
-    assert l.ttvdm_abi_version() == 1
+    assert l.ttvdm_abi_version() == 3
     assert lib.launch_count() == 0 or lib.launch_count() > 0
 
 
@@ -33,14 +33,14 @@ def test_ctypes_structs_match_header_sizes(tmp_path):
     """Compile a tiny C program against include/ttvdm.h and compare sizeof() with the ctypes mirrors."""
     from this_and_that_vdm_b200 import lib
     src = tmp_path / "sz.c"
-    names = ["gemm", "attn", "xattn", "tattn", "groupnorm", "layernorm", "prepare", "euler"]
+    names = ["gemm", "attn", "xattn", "tattn", "groupnorm", "layernorm", "prepare", "euler", "pack_linear"]
     body = "".join(f'printf("%zu\\n", sizeof(ttvdm_{n}_params));' for n in names)
     src.write_text(f'#include <stdio.h>\n#include "ttvdm.h"\nint main(){{{body}return 0;}}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     mirrors = [lib.GemmParams, lib.AttnParams, lib.XAttnParams, lib.TAttnParams, lib.GroupNormParams,
-               lib.LayerNormParams, lib.PrepareParams, lib.EulerParams]
+               lib.LayerNormParams, lib.PrepareParams, lib.EulerParams, lib.PackLinearParams]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
@@ -150,16 +150,25 @@ def test_pipeline_argument_errors():
 
 
 def test_weight_packing_layouts():
-    """Packing used by the engine: GEGLU interleave and conv tap-major layout (pure tensor logic, CPU)."""
-    from this_and_that_vdm_b200.engine import _pack_conv3x3, _pack_geglu, _pack_tconv
-    w = torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3)
-    b = torch.arange(8, dtype=torch.float32)
-    wi, bi = _pack_geglu(w, b, "cpu")
-    assert bi.tolist() == [0, 4, 1, 5, 2, 6, 3, 7]
-    assert torch.equal(wi.float()[0], w[0]) and torch.equal(wi.float()[1], w[4])
-    cw = torch.randn(5, 8, 3, 3)
-    pk = _pack_conv3x3(cw, "cpu", pad_cin=64).float().reshape(5, 3, 3, 64)
-    assert torch.allclose(pk[..., :8], cw.permute(0, 2, 3, 1).to(torch.bfloat16).float()) and float(pk[..., 8:].abs().max()) == 0
-    tw = torch.randn(4, 4, 3, 1, 1)
-    tp = _pack_tconv(tw, "cpu").float().reshape(4, 3, 4)
-    assert torch.allclose(tp[:, 1, :], tw[:, :, 1, 0, 0].to(torch.bfloat16).float())
+    """Layouts the engine asks the repack entry points for (ttvdm_pack_*; here through the CPU emulation of the C ABI):
+    GEGLU interleave with LayerNorm fold, conv tap-major layout with channel padding, fused q|k|v rows."""
+    from tests import fake_lib
+    from this_and_that_vdm_b200.engine import _fold_ln, _pack_conv
+    with fake_lib.installed():
+        w = torch.arange(8 * 32, dtype=torch.float32).reshape(8, 32) / 64
+        b = torch.arange(8, dtype=torch.float32)
+        gamma, beta = torch.full((32,), 2.0), torch.full((32,), 0.5)
+        wi, bi, cs = _fold_ln([w], b, gamma, beta, "cpu", geglu=True)
+        order = [0, 4, 1, 5, 2, 6, 3, 7]
+        assert torch.equal(wi.float(), (2 * w)[order].to(torch.bfloat16).float())
+        assert torch.allclose(bi, (b + 0.5 * w.sum(1))[order]) and torch.allclose(cs, wi.float().sum(1))
+        q, k, v = torch.randn(4, 32), torch.randn(4, 32), torch.randn(4, 32)
+        wqkv, bq, _ = _fold_ln([q, k, v], None, torch.ones(32), torch.zeros(32), "cpu")
+        assert torch.equal(wqkv.float(), torch.cat([q, k, v]).to(torch.bfloat16).float()) and float(bq.abs().max()) == 0
+        cw = torch.randn(5, 8, 3, 3)
+        pk = _pack_conv(cw, "cpu", pad_cin=64).float().reshape(5, 3, 3, 64)
+        assert torch.allclose(pk[..., :8], cw.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+        assert float(pk[..., 8:].abs().max()) == 0
+        tw = torch.randn(4, 4, 3, 1, 1)
+        tp = _pack_conv(tw, "cpu").float().reshape(4, 3, 4)
+        assert torch.allclose(tp[:, 1, :], tw[:, :, 1, 0, 0].to(torch.bfloat16).float())

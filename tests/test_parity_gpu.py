@@ -223,3 +223,138 @@ def test_svd_config_forward_vs_oracle():
         eager = _eager_bf16(lambda s, *a: O.unet_forward(s[0], cfg, *a), [usd], sample, T0, ehs, ati)
     e, ee = rel_l2(out, ref), rel_l2(eager, ref)
     assert e <= ee + 1e-3 and e < CAP, (e, ee)
+
+
+# ====================================================================================================================
+# BASELINE.json configurations at SVD width ("Next" #1 ii): the goldens are oracle outputs committed by
+# tests/golden/make_baseline_golden.py (oracle pinned to the reference's own forward by tests/test_reference_pin.py) or
+# outputs of the reference's own classes (tests/golden/reference_pin.pt). Weights: tests/refpin.py (pure function of the
+# parameter name), so nothing but the expected outputs travels. Measured values are recorded in DESIGN.md §7.
+# ====================================================================================================================
+SVD_FWD_CAP = 3e-2      # one forward, bf16 storage / fp32 accumulate vs fp32 (measured 0.8e-2 .. 1.3e-2)
+SVD_LOOP_CAP = 6e-2     # 25 compounding Euler steps (measured: see DESIGN.md §7)
+
+
+@pytest.fixture(scope="module")
+def svd_refpin():
+    """SVD-config UNet + GestureNet with the deterministic tests/refpin.py weights, on the GPU."""
+    from svd.temporal_controlnet import ControlNetModel
+    from svd.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    from tests import refpin
+    kind = refpin.CASES["svd"][0]
+    unet = UNetSpatioTemporalConditionModel(num_frames=14, **kind).eval()
+    cn = ControlNetModel(**kind).eval()
+    unet.load_state_dict(refpin.fill_state_dict(((k, v.shape) for k, v in unet.state_dict().items()), seed=11))
+    cn.load_state_dict(refpin.fill_state_dict(((k, v.shape) for k, v in cn.state_dict().items()), seed=12))
+    return unet.to("cuda"), cn.to("cuda")
+
+
+@pytest.mark.slow
+def test_svd_b2_unet_gesturenet_vs_reference_own_forward(svd_refpin):
+    """SVD widths, B = 2 (the T5 context quirk is live), 14 x 16 x 24: the sm_100a engine against the outputs of the
+    REFERENCE'S OWN UNetSpatioTemporalConditionModel / ControlNetModel forward (tests/golden/reference_pin.pt)."""
+    from tests import refpin
+    unet, cn = svd_refpin
+    gold = torch.load(GOLD / "reference_pin.pt", weights_only=False)["svd"]
+    _, B, F, h, w = refpin.CASES["svd"]
+    sample, ehs, ati, cond = refpin.make_inputs(B, F, h, w)
+    cc = torch.cat([cond] * B)
+    t = torch.tensor(refpin.TIMESTEP)
+    with torch.no_grad():
+        y = unet(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda()).sample
+        d, m = cn(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda(), controlnet_cond=cc.cuda(), conditioning_scale=0.75,
+                  return_dict=False)
+        yg = unet(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda(), down_block_additional_residuals=d,
+                  mid_block_additional_residual=m).sample
+    errs = {"unet": rel_l2(y, gold["unet"]), "cn_mid": rel_l2(m, gold["cn_mid"]), "vgl": rel_l2(yg, gold["vgl"])}
+    print("svd B=2 vs reference forward:", errs)
+    assert all(v < SVD_FWD_CAP for v in errs.values()), errs
+
+
+@pytest.mark.slow
+def test_svd_b2_fused_step_32x48_vs_oracle(svd_refpin):
+    """BASELINE configs[0] size (14 x 32 x 48 latent) with B = 2: UNet + GestureNet through the fused sampler path
+    (zero-conv accumulation into the skips, epilogue-fused norms) against the fp32 oracle computed here."""
+    from tests import refpin
+    from tests.test_reference_pin import _models
+    from this_and_that_vdm_b200.sampler import FusedDenoiser
+    unet, cn = svd_refpin
+    usd, csd = _models(refpin.CASES["svd"][0], 14)
+    cfg = dict(O.SVD_CONFIG)
+    F, h, w = 14, 32, 48
+    sample, ehs, ati, cond = refpin.make_inputs(2, F, h, w, seed=3)
+    sig = O.karras_sigmas(25)
+    ts = O.euler_timesteps(sig)
+    i = 9
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(1, F, 4, h, w, generator=g) * float(sig[i])
+    img = torch.randn(1, 4, h, w, generator=g)
+    img2 = torch.cat([torch.zeros_like(img), img])
+    with torch.no_grad():
+        x = torch.cat([torch.cat([lat] * 2) / (float(sig[i]) ** 2 + 1) ** 0.5, img2[:, None].repeat(1, F, 1, 1, 1)], dim=2)
+        d, m = O.controlnet_forward(csd, cfg, x, ts[i], ehs, ati, torch.cat([cond, cond]), 1.0)
+        ref = O.unet_forward(usd, cfg, x, ts[i], ehs, ati, d, m)
+        den = FusedDenoiser(unet._get_engine(), cn._get_engine())
+        den.prepare(ehs.cuda(), img2.cuda(), ati.cuda(), sig, ts, torch.linspace(1, 3, F), num_frames=F, height=h,
+                    width=w, controlnet_cond=cond.cuda())
+        eps = den.predict(i, lat[0].cuda().contiguous())
+    e = rel_l2(eps.view(2, F, h, w, 4).permute(0, 1, 4, 2, 3), ref)
+    print("svd B=2 fused VGL step 14x32x48 vs oracle:", e)
+    assert e < SVD_FWD_CAP, e
+
+
+def _run_loop(unet, cn, vgl: bool):
+    from svd.pipeline_stable_video_diffusion import StableVideoDiffusionPipeline
+    from svd.pipeline_stable_video_diffusion_controlnet import StableVideoDiffusionControlNetPipeline
+    from tests.golden.make_baseline_golden import KEEP_STEPS, loop_inputs
+    noise, img2, ehs, ati, cond = loop_inputs()
+    F, h, w = 14, 32, 48
+    kept = {}
+
+    def cb(pipe, i, t, kw):
+        if i + 1 in KEEP_STEPS:
+            kept[f"step{i + 1}"] = kw["latents"].detach().float().cpu().clone()
+        return {}
+
+    common = dict(height=h * 8, width=w * 8, num_frames=F, num_inference_steps=25, min_guidance_scale=1.0,
+                  max_guidance_scale=3.0, fps=7, motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent",
+                  latents=noise.cuda(), encoder_hidden_states=ehs.cuda(), image_latents=img2.cuda(),
+                  callback_on_step_end=cb, callback_on_step_end_tensor_inputs=["latents"])
+    if vgl:
+        pipe = StableVideoDiffusionControlNetPipeline.from_pretrained("unused", unet=unet).to("cuda")
+        out = pipe(controlnet=cn, guess_mode=False, controlnet_cond_latents=cond.cuda(), **common).frames
+    else:
+        pipe = StableVideoDiffusionPipeline.from_pretrained("unused", unet=unet).to("cuda")
+        out = pipe(**common).frames
+    kept["final"] = out.float().cpu()
+    return kept
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("vgl", [False, True], ids=["vl25", "vgl25"])
+def test_25_step_256x384_svd_width_vs_golden(svd_refpin, vgl):
+    """BASELINE.json configs[1] / configs[2]: the full 25-step Euler loop at 14 x 256 x 384, SVD widths, through the
+    drop-in pipeline __call__, against the committed oracle trajectory (latents after steps 1, 5, 12 and 25)."""
+    unet, cn = svd_refpin
+    name = "vgl25" if vgl else "vl25"
+    gold = torch.load(GOLD / f"baseline_{name}.pt")
+    kept = _run_loop(unet, cn, vgl)
+    errs = {k: rel_l2(kept[k if k != "step25" else "final"], v) for k, v in gold.items()}
+    print(f"{name} 14x256x384 SVD width, rel-L2 per kept step:", errs)
+    assert rel_l2(kept["final"], gold["step25"]) < SVD_LOOP_CAP, errs
+    assert errs["step1"] < 1e-3  # sigma 700: the state is dominated by the (exact, fp32) Euler arithmetic
+
+
+@pytest.mark.slow
+def test_unet_forward_72x128_b1_vs_golden(svd_refpin):
+    """One UNet forward at the headline resolution (14 x 576 x 1024 -> latent 72 x 128): real tile counts, conv halo at
+    W = 128, S = 9216 attention, odd CTA-pair tails — against the committed oracle output."""
+    from tests import refpin
+    unet, _ = svd_refpin
+    gold = torch.load(GOLD / "baseline_fwd72.pt")["unet"]
+    sample, ehs, ati, _ = refpin.make_inputs(1, 14, 72, 128, seed=31)
+    with torch.no_grad():
+        y = unet(sample.cuda(), refpin.TIMESTEP, ehs.cuda(), ati.cuda()).sample
+    e = rel_l2(y, gold)
+    print("UNet forward 14x72x128 B=1 vs oracle golden:", e)
+    assert y.shape == gold.shape and e < SVD_FWD_CAP, e

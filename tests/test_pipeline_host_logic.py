@@ -165,3 +165,26 @@ def test_vgl_pipeline_with_fp16_modules(cpu_engines):
         ref, _ = PC.run_oracle(sds, latent_dtype=torch.float16)
     want = (ref[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert frames[0].dtype == torch.float32 and rel_l2(frames[0], want) < 5e-2
+
+
+def test_preprocess_image_tensor_inputs_follow_vae_image_processor():
+    """tensor images are a documented input of __call__. diffusers' VaeImageProcessor.preprocess —
+    which the reference calls at svd/pipeline_stable_video_diffusion_controlnet.py:541 — stacks / concatenates them,
+    resizes to (height, width), maps [0,1] -> [-1,1] unless the tensor already has negative values, and passes 4-channel
+    latents through untouched."""
+    import torch
+    from svd.pipeline_common import SVDPipelineBase as P
+    pre = lambda im, h, w: P._preprocess_image(None, im, h, w)  # noqa: E731
+    g = torch.Generator().manual_seed(0)
+    x01 = torch.rand(1, 3, 16, 24, generator=g)
+    out = pre(x01, 32, 48)
+    assert out.shape == (1, 3, 32, 48)
+    assert torch.allclose(out, 2.0 * torch.nn.functional.interpolate(x01, size=(32, 48)) - 1.0)
+    assert float(out.min()) < 0 and float(out.max()) <= 1.0
+    xs = x01 * 2 - 1                        # already in [-1, 1]: not normalised again
+    assert torch.equal(pre(xs, 16, 24), xs)
+    lst = [torch.rand(3, 16, 24, generator=g), torch.rand(3, 16, 24, generator=g)]   # list of 3-D tensors: stacked
+    out = pre(lst, 16, 24)
+    assert out.shape == (2, 3, 16, 24) and torch.allclose(out, 2 * torch.stack(lst) - 1)
+    lat = torch.randn(2, 4, 8, 8, generator=g)   # latents: returned as they are
+    assert torch.equal(pre(lat, 64, 64), lat)

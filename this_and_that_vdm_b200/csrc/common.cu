@@ -9,7 +9,8 @@ thread_local char g_err[512] = {0};
 std::atomic<uint64_t> g_launches{0};
 int g_num_sms = 0;
 static EncodeTiledFn g_encode = nullptr;
-static std::once_flag g_once;
+static std::mutex g_init_mutex;
+static bool g_inited = false;
 static int g_init_status = 0;
 
 EncodeTiledFn encode_tiled_fn() { return g_encode; }
@@ -44,8 +45,20 @@ static void do_init() {
 }
 
 int ensure_init() {
-  std::call_once(g_once, do_init);
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (!g_inited) {
+    do_init();
+    g_inited = g_init_status == 0;  // a failed init (no device yet, wrong arch) is retried by the next call
+  }
   return g_init_status;
+}
+
+void reset_init() {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  g_inited = false;
+  g_encode = nullptr;
+  g_num_sms = 0;
+  g_init_status = 0;
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -89,7 +102,14 @@ int ttvdm_last_error(char* buf, size_t n) {
   return 0;
 }
 
-int ttvdm_abi_version(void) { return 1; }
+// Drops the process-wide immutable state (driver entry point, SM count). The library owns no device memory, streams or
+// events, so there is nothing else to release; the next call (or ttvdm_init) initialises again.
+int ttvdm_destroy(void) {
+  ttvdm::reset_init();
+  return 0;
+}
+
+int ttvdm_abi_version(void) { return 3; }
 
 uint64_t ttvdm_launch_count(void) { return ttvdm::g_launches.load(); }
 }

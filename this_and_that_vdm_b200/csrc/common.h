@@ -30,6 +30,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();
 int ensure_init();
+void reset_init();
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -54,7 +54,46 @@ struct GemmArgs {
   int ctas_per_n;     // b_resident: CTAs sharing an N tile
   int tma_epi;        // 1: residual tile in / output tile out through per-warp smem + TMA (coalesced, asynchronous)
   int epi_box_w;      // CONV: pixels per image row covered by a warp's 32 tile rows (min(TW, 32))
+  // normalisation fusions (see include/ttvdm.h)
+  double* gn_stats;   // [M / gn_rpi][N / 2][2]: per (group instance, channel pair) sum / sum of squares of the stored bf16 values
+  int gn_rpi;
+  float* row_sums;    // [N / 32][M][2]: per row and 32-column chunk, sum / sum of squares of the stored bf16 values
+                      // (LayerNorm of the consumer; plain stores, no atomics: every (chunk, row) has exactly one writer)
+  int ln_parts;       // consumer: chunks per row in ln_rowsums (= K / 32)
+  int contig;         // 1: a CTA walks a CONTIGUOUS range of tiles (few group instances per CTA -> few statistics flushes)
+  int tiles_per_cta;
+  const float* rs_addvec;  // [rs_add_mod][ld_rs_add] added to the stored values inside the row sums only
+  int rs_add_rows, rs_add_mod, ld_rs_add;
+  const float* ln_rowsums;  // consumer side: [M][2] of the A operand -> LayerNorm folded into this epilogue
+  const float* ln_colsum;   // [N]
+  const float* prevec;      // [prevec_mod][ldpv] added to the accumulator before the LayerNorm scale
+  const float* ln_row_add;  // [prevec_mod][2]
+  int prevec_rows, prevec_mod, ldpv;
+  float ln_inv_k, ln_eps;
 };
+
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f32x2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// Column sums over the 32 lanes of a warp: lane r holds v[0..32) = 32 consecutive columns of row r; on return v[0] of
+// lane c is sum_r v_r[c]. Recursive halving: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h];
+      const float keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
 
 struct TileCoord {
   int n0;          // first output column
@@ -96,18 +135,64 @@ template <int kCtas>
 __device__ __forceinline__ int sched_tile(const GemmArgs& g, int i, int cta_rank) {
   if (kCtas == 2) {
     // CTA pair: both CTAs walk the same pair-tiles; CTA r owns M tile 2*pm + r (may be one past the end: all-padding tile)
-    const int pt = ((int)blockIdx.x >> 1) + i * ((int)gridDim.x >> 1);
     const int pm_tiles = (g.m_tiles + 1) >> 1;
+    int pt;
+    if (g.contig) {
+      if (i >= g.tiles_per_cta) return -1;
+      pt = ((int)blockIdx.x >> 1) * g.tiles_per_cta + i;
+    } else {
+      pt = ((int)blockIdx.x >> 1) + i * ((int)gridDim.x >> 1);
+    }
     if (pt >= pm_tiles * g.n_tiles) return -1;
     const int pm = pt / g.n_tiles;
     return (2 * pm + cta_rank) * g.n_tiles + (pt - pm * g.n_tiles);
   }
   if (!g.b_resident) {
-    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    int tile;
+    if (g.contig) {
+      if (i >= g.tiles_per_cta) return -1;
+      tile = (int)blockIdx.x * g.tiles_per_cta + i;
+    } else {
+      tile = (int)blockIdx.x + i * (int)gridDim.x;
+    }
     return tile < g.m_tiles * g.n_tiles ? tile : -1;
   }
-  const int mt = (int)blockIdx.x / g.n_tiles + i * g.ctas_per_n;
+  int mt;
+  if (g.contig) {
+    if (i >= g.tiles_per_cta) return -1;
+    mt = ((int)blockIdx.x / g.n_tiles) * g.tiles_per_cta + i;
+  } else {
+    mt = (int)blockIdx.x / g.n_tiles + i * g.ctas_per_n;
+  }
   return mt < g.m_tiles ? mt * g.n_tiles + ((int)blockIdx.x % g.n_tiles) : -1;
+}
+
+// Group instance of a tile if all of its rows lie in ONE instance (then its statistics go through the CTA's shared-memory
+// accumulators), else -1 (LINEAR tiles at the low-resolution levels can straddle instances: direct global atomics).
+__device__ __forceinline__ int tile_instance(const GemmArgs& g, const TileCoord& t) {
+  if (g.mode == TTVDM_A_LINEAR) {
+    const long long last = min((long long)t.m0 + kBlockM - 1, (long long)g.M - 1);
+    const int a = t.m0 / g.gn_rpi, b = (int)(last / g.gn_rpi);
+    return a == b ? a : -1;
+  }
+  if (t.img >= g.n_img) return -2;  // all-padding tile of an odd CTA pair: nothing to add
+  if (g.mode == TTVDM_A_CONV3X3) return (int)(((long long)t.img * g.H * g.W) / g.gn_rpi);
+  return (int)((((long long)t.img * g.H + t.h0) * g.W) / g.gn_rpi);
+}
+
+// Epilogue warps only (kEpiWarps * 32 threads, named barrier 1): add the CTA's shared-memory GroupNorm accumulators
+// ([N / 2][2] floats: per channel pair sum / sum of squares over the tiles seen since the last flush) to the global fp64
+// bins of instance `inst`, and clear them.
+__device__ __forceinline__ void gn_flush(const GemmArgs& g, float* acc, int inst, int epi_tid) {
+  named_bar_sync(1, kEpiWarps * 32);
+  if (inst >= 0) {
+    for (int i = epi_tid; i < g.N; i += kEpiWarps * 32) {
+      const float v = acc[i];
+      if (v != 0.f) red_add_f64(g.gn_stats + (long long)inst * g.N + i, (double)v);
+      acc[i] = 0.f;
+    }
+  }
+  named_bar_sync(1, kEpiWarps * 32);
 }
 
 // Returns 2 * gelu(x) = x + |x| * erf(|x| / sqrt(2)) (the caller folds the 0.5 into its own scale factor).
@@ -128,10 +213,61 @@ __device__ __forceinline__ float gelu_erf_x2(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * gelu_erf_x2(x); }
 
+// fp64 atomics of one 32-column chunk's per-pair GroupNorm sums: `a` = the bf16-rounded values of this lane's row
+// (zeros for rows that do not exist), inst0..inst1 = group instances touched by the warp's 32 rows.
+// GroupNorm sums of one 32-column chunk held one row per lane (`a` = the bf16-rounded values, anything for rows that do
+// not exist). ALL 32 lanes must call this. acc != nullptr: the tile lies in one instance -> shared-memory accumulators;
+// else one reduction per instance present in the warp's rows, straight to the global fp64 bins.
+__device__ __forceinline__ void gn_stats_chunk(const GemmArgs& g, const float (&a)[32], bool valid, long long row, int col0,
+                                               int lane, float* acc) {
+  const int col = col0 + lane;
+  if (acc != nullptr) {
+    float q[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = valid ? a[i] * a[i] : 0.f;
+    const float cq = warp_colsum32(q, lane);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = valid ? a[i] : 0.f;
+    const float cs = warp_colsum32(q, lane);
+    if (col < g.N) {  // lane c holds column col0 + c; bins are per channel PAIR: (sum, sum of squares)
+      atomicAdd(acc + (col >> 1) * 2, cs);
+      atomicAdd(acc + (col >> 1) * 2 + 1, cq);
+    }
+    return;
+  }
+  const int mine = valid ? (int)(row / g.gn_rpi) : -1;
+  int imin = valid ? mine : 0x7fffffff, imax = mine;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+    imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+  }
+  if (imax < 0) return;  // no valid row in this warp (warp-uniform)
+  for (int inst = imin; inst <= imax; ++inst) {
+    const bool in = valid && mine == inst;
+    float q[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = in ? a[i] * a[i] : 0.f;
+    const float cq = warp_colsum32(q, lane);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = in ? a[i] : 0.f;
+    const float cs = warp_colsum32(q, lane);
+    if (col < g.N) {
+      double* dst = g.gn_stats + (long long)inst * g.N + (col >> 1) * 2;
+      red_add_f64(dst, (double)cs);
+      red_add_f64(dst + 1, (double)cq);
+    }
+  }
+}
+
+// Direct epilogue of one 32-column chunk (one row per lane). Every lane of the warp calls it (rows that do not exist
+// with valid = false): the GroupNorm statistics are a warp-wide reduction.
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], long long out_row, int col0,
-                                               const float* rv) {
-    float a[32];
-    const bool full = (col0 + 32 <= g.N) && ((g.N & 7) == 0);
+                                               const float* rv, bool valid, int lane, float* gn_acc) {
+  float a[32];
+  const bool full = (col0 + 32 <= g.N) && ((g.N & 7) == 0);
+  const bool stats = (g.gn_stats != nullptr || g.row_sums != nullptr) && full && !g.out_fp32 && !g.geglu;
+  if (valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
     if (g.bias != nullptr) {
@@ -181,77 +317,102 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
             o[j] = __float2bfloat16((j & 1) ? f.y : f.x);
           }
       }
-      return;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] *= g.s0;
-    if (g.res1 != nullptr) {
-      const __nv_bfloat16* rp = g.res1 + out_row * g.ldr1 + col0;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16(w4[j]);
-            a[i * 8 + j * 2] += g.s1 * f.x;
-            a[i * 8 + j * 2 + 1] += g.s1 * f.y;
-          }
-        }
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < g.N) a[i] += g.s1 * __bfloat162float(rp[i]);
-      }
-    }
-    if (g.res2 != nullptr) {
-      const __nv_bfloat16* rp = g.res2 + out_row * g.ldr2 + col0;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16(w4[j]);
-            a[i * 8 + j * 2] += g.s2 * f.x;
-            a[i * 8 + j * 2 + 1] += g.s2 * f.y;
-          }
-        }
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < g.N) a[i] += g.s2 * __bfloat162float(rp[i]);
-      }
-    }
-    if (g.act == 1) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = a[i] / (1.f + __expf(-a[i]));
-    }
-    if (g.out_fp32) {
-      float* o = reinterpret_cast<float*>(g.out) + out_row * g.ldo + col0;
-      if (full && (g.ldo & 3) == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < g.N) o[i] = a[i];
-      }
     } else {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col0;
-      if (full) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          *(reinterpret_cast<uint4*>(o) + i) =
-              make_uint4(pack_bf16(a[i * 8], a[i * 8 + 1]), pack_bf16(a[i * 8 + 2], a[i * 8 + 3]),
-                         pack_bf16(a[i * 8 + 4], a[i * 8 + 5]), pack_bf16(a[i * 8 + 6], a[i * 8 + 7]));
+      for (int i = 0; i < 32; ++i) a[i] *= g.s0;
+      if (g.res1 != nullptr) {
+        const __nv_bfloat16* rp = g.res1 + out_row * g.ldr1 + col0;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16(w4[j]);
+              a[i * 8 + j * 2] += g.s1 * f.x;
+              a[i * 8 + j * 2 + 1] += g.s1 * f.y;
+            }
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < g.N) a[i] += g.s1 * __bfloat162float(rp[i]);
+        }
+      }
+      if (g.res2 != nullptr) {
+        const __nv_bfloat16* rp = g.res2 + out_row * g.ldr2 + col0;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16(w4[j]);
+              a[i * 8 + j * 2] += g.s2 * f.x;
+              a[i * 8 + j * 2 + 1] += g.s2 * f.y;
+            }
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < g.N) a[i] += g.s2 * __bfloat162float(rp[i]);
+        }
+      }
+      if (g.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = a[i] / (1.f + __expf(-a[i]));
+      }
+      if (g.out_fp32) {
+        float* o = reinterpret_cast<float*>(g.out) + out_row * g.ldo + col0;
+        if (full && (g.ldo & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < g.N) o[i] = a[i];
         }
       } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < g.N) o[i] = __float2bfloat16(a[i]);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + out_row * g.ldo + col0;
+        if (full) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(a[2 * i], a[2 * i + 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *(reinterpret_cast<uint4*>(o) + i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          if (stats) {
+            // statistics of exactly what the consumer will read: the bf16-rounded values
+            float rs = 0.f, rq = 0.f;
+            const float* av = (g.row_sums != nullptr && g.rs_addvec != nullptr)
+                                  ? g.rs_addvec + (long long)((out_row / g.rs_add_rows) % g.rs_add_mod) * g.ld_rs_add + col0
+                                  : nullptr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 f = unpack_bf16(pk[i]);
+              a[2 * i] = f.x;
+              a[2 * i + 1] = f.y;
+              float2 e = f;
+              if (av != nullptr) {
+                const float2 d = __ldg(reinterpret_cast<const float2*>(av) + i);
+                e.x += d.x;
+                e.y += d.y;
+              }
+              rs += e.x + e.y;
+              rq = fmaf(e.x, e.x, fmaf(e.y, e.y, rq));
+            }
+            if (g.row_sums != nullptr)
+              *reinterpret_cast<float2*>(g.row_sums + ((long long)(col0 >> 5) * g.M + out_row) * 2) = make_float2(rs, rq);
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < g.N) o[i] = __float2bfloat16(a[i]);
+        }
       }
     }
   }
+  if (stats && g.gn_stats != nullptr) gn_stats_chunk(g, a, valid, out_row, col0, lane, gn_acc);  // whole warp
+}
 
 template <int kCtas>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -275,6 +436,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int cta_rank = kCtas == 2 ? (int)cluster_ctarank() : 0;
   // b_resident only: the pinned W tile sits behind the operand ring and the TMA-epilogue staging buffers
   uint8_t* bres = tiles + g.stages * stage_bytes + (g.tma_epi ? kEpiWarps * kEpiBufBytes : 0);
+  // GroupNorm accumulators of this CTA ([N / 2][2] floats), behind everything else
+  float* gn_acc_base = reinterpret_cast<float*>(bres + (g.b_resident ? g.taps * g.kc_per_tap * b_chunk_bytes : 0));
+  if (g.gn_stats != nullptr)
+    for (int i = threadIdx.x; i < g.N; i += kNumThreads) gn_acc_base[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -413,6 +578,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = (warp - 4) >> 2;  // which 32-column chunks (ch % kNumEpiGroups == grp)
     const int chunks = g.block_n / 32;
+    const int epi_tid = threadIdx.x - 128;
+    int cur_inst = -1;  // group instance whose sums sit in gn_acc_base (same value in every epilogue thread)
     if (g.tma_epi) {
       // ---- TMA epilogue: each warp owns a 32-row x 64-column strip per tile. The residual strip is fetched by TMA
       // into the warp's 128B-swizzled staging buffer while the tile's MMAs run, the fp32 epilogue math happens in
@@ -433,6 +600,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const TileCoord t = tile_coord(g, tile);
         const int col0 = t.n0 + strip;
         const bool active = (strip < g.block_n) && (col0 < g.N);
+        float* gn_acc = nullptr;
+        if (g.gn_stats != nullptr) {
+          const int ti = tile_instance(g, t);
+          if (ti >= 0) {
+            if (ti != cur_inst) {
+              if (cur_inst >= 0) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
+              cur_inst = ti;
+            }
+            gn_acc = gn_acc_base;
+          }
+        }
         // box coordinates of the warp's 32 tile rows
         int c1, c2 = 0, c3 = 0;
         if (g.mode == TTVDM_A_LINEAR) {
@@ -476,6 +654,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         const float* rv = nullptr;
         if (g.rowvec != nullptr && my_valid) rv = g.rowvec + (my_row / g.rows_per_vec) * g.ldrv;
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        const float* pv = nullptr;
+        if (g.ln_rowsums != nullptr && my_valid) {
+          float2 rs = make_float2(0.f, 0.f);
+          for (int j = 0; j < g.ln_parts; ++j) {  // [K / 32][M][2]: coalesced across the warp's 32 rows
+            const float2 pj = __ldg(reinterpret_cast<const float2*>(g.ln_rowsums) + (long long)j * g.M + my_row);
+            rs.x += pj.x;
+            rs.y += pj.y;
+          }
+          if (g.prevec_mod > 0) {
+            const int pi = (int)((my_row / g.prevec_rows) % g.prevec_mod);
+            if (g.prevec != nullptr) pv = g.prevec + (long long)pi * g.ldpv;
+            if (g.ln_row_add != nullptr) {
+              const float2 ra = __ldg(reinterpret_cast<const float2*>(g.ln_row_add) + pi);
+              rs.x += ra.x;
+              rs.y += ra.y;
+            }
+          }
+          ln_mean = rs.x * g.ln_inv_k;
+          ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, rs.y * g.ln_inv_k), 0.f) + g.ln_eps);
+        }
+        float row_s = 0.f, row_q = 0.f;  // LayerNorm sums of this lane's row over the warp's strip
+        const float* rs_av = (g.row_sums != nullptr && g.rs_addvec != nullptr && my_valid)
+                                 ? g.rs_addvec + (long long)((my_row / g.rs_add_rows) % g.rs_add_mod) * g.ld_rs_add
+                                 : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         if (active) {
@@ -494,6 +697,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float a[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
+            if (g.ln_rowsums != nullptr && gc + 32 <= g.N) {
+              // LayerNorm of the A operand folded in: rstd * (acc + prevec - mean * colsum) (bias is added below)
+              if (pv != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(pv + gc + i));
+                  a[i] += b4.x; a[i + 1] += b4.y; a[i + 2] += b4.z; a[i + 3] += b4.w;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.ln_colsum + gc + i));
+                a[i] = ln_rstd * fmaf(-ln_mean, c4.x, a[i]);
+                a[i + 1] = ln_rstd * fmaf(-ln_mean, c4.y, a[i + 1]);
+                a[i + 2] = ln_rstd * fmaf(-ln_mean, c4.z, a[i + 2]);
+                a[i + 3] = ln_rstd * fmaf(-ln_mean, c4.w, a[i + 3]);
+              }
+            }
             if (gc + 32 <= g.N) {
               if (g.bias != nullptr) {
 #pragma unroll
@@ -567,7 +788,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o[k] = o[k] / (1.f + __expf(-o[k]));
               }
-              *sp = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+              const uint4 pk4 = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+              *sp = pk4;
+              if (g.row_sums != nullptr) {
+                const uint32_t w4[4] = {pk4.x, pk4.y, pk4.z, pk4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = unpack_bf16(w4[k]);  // the rounded values the consumer will read
+                  if (rs_av != nullptr) {
+                    const float2 d = __ldg(reinterpret_cast<const float2*>(rs_av + gc + pc * 8) + k);
+                    f.x += d.x;
+                    f.y += d.y;
+                  }
+                  row_s += f.x + f.y;
+                  row_q = fmaf(f.x, f.x, fmaf(f.y, f.y, row_q));
+                }
+              }
+            }
+            if (g.row_sums != nullptr && my_valid && gc + 32 <= g.N) {
+              // one (32-column chunk, row) slot per lane: 32 consecutive rows = one 256-byte store, no atomics
+              *reinterpret_cast<float2*>(g.row_sums + ((long long)(gc >> 5) * g.M + my_row) * 2) = make_float2(row_s, row_q);
+              row_s = row_q = 0.f;
             }
           }
         }
@@ -585,9 +826,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             else tma_store_4d(&tmOut, sbuf, col0, c1, c2, c3);
             tma_store_commit();
           }
+          if (g.gn_stats != nullptr) {
+            // GroupNorm statistics of the strip from the staged bf16 values: lane l owns the channel pair (2l, 2l+1) of
+            // the strip and walks the 32 rows (one conflict-free 128-byte row read per step: the 16-byte piece holding
+            // the pair sits at ((l >> 2) ^ (r & 7))), then adds to the (instance, pair) bins with fp64 atomics. Rows are
+            // in ascending order inside the strip, so group instances form runs.
+            const uint32_t vmask = __ballot_sync(0xffffffffu, my_valid);
+            const int inst_l = my_valid ? (int)(my_row / g.gn_rpi) : -1;
+            const int pair_col = col0 + 2 * lane;
+            const bool col_ok = pair_col < g.N && (2 * lane < g.block_n - strip);
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            int cur = -1;
+            const uint8_t* sb = sbuf + (lane & 3) * 4;
+            for (int r = 0; r < 32; ++r) {
+              const int ir = __shfl_sync(0xffffffffu, inst_l, r);
+              if (!((vmask >> r) & 1u)) continue;  // warp-uniform
+              if (ir != cur) {
+                if (cur >= 0 && col_ok) {
+                  double* dst = g.gn_stats + ((long long)cur * (g.N >> 1) + (pair_col >> 1)) * 2;
+                  red_add_f64(dst, (double)(s0 + s1));
+                  red_add_f64(dst + 1, (double)(q0 + q1));
+                }
+                s0 = s1 = q0 = q1 = 0.f;
+                cur = ir;
+              }
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(sb + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
+              const float2 f = unpack_bf16(u);
+              s0 += f.x; s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            }
+            if (cur >= 0 && col_ok) {
+              if (gn_acc != nullptr) {  // the whole tile lies in `cur`: CTA-level accumulators, flushed on instance change
+                atomicAdd(gn_acc + pair_col, s0 + s1);
+                atomicAdd(gn_acc + pair_col + 1, q0 + q1);
+              } else {
+                double* dst = g.gn_stats + ((long long)cur * (g.N >> 1) + (pair_col >> 1)) * 2;
+                red_add_f64(dst, (double)(s0 + s1));
+                red_add_f64(dst + 1, (double)(q0 + q1));
+              }
+            }
+            __syncwarp();  // every lane has read the strip before lane 0 may let the next tile's residual land in it
+          }
         }
       }
       if (lane == 0) tma_store_wait_read();
+      if (g.gn_stats != nullptr) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
     } else {
     int it = 0;
     for (;; ++it) {
@@ -614,6 +897,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       const float* rv = nullptr;
       if (g.rowvec != nullptr && valid) rv = g.rowvec + (out_row / g.rows_per_vec) * g.ldrv;
+      float* gn_acc = nullptr;
+      if (g.gn_stats != nullptr) {
+        const int ti = tile_instance(g, t);
+        if (ti >= 0) {
+          if (ti != cur_inst) {
+            if (cur_inst >= 0) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
+            cur_inst = ti;
+          }
+          gn_acc = gn_acc_base;
+        }
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -622,7 +916,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kAccCols + ch * 32, v);
         tmem_ld_wait();
         const int col0 = t.n0 + ch * 32;
-        if (valid && col0 < g.N) epilogue_chunk(g, v, out_row, col0, rv);
+        if (col0 < g.N) epilogue_chunk(g, v, out_row, col0, rv, valid, lane, gn_acc);  // col0 is warp-uniform
         __syncwarp();
       }
       tc_fence_before();
@@ -632,6 +926,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else mbar_arrive_cluster(&tempty_bar[acc], 0);
       }
     }
+    if (g.gn_stats != nullptr) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
       }
   }
 
@@ -673,6 +968,22 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (p->rowvec && p->ldrv > 0 && (p->ldrv % 4 != 0 || (reinterpret_cast<uintptr_t>(p->rowvec) & 15)))
     return fail(TTVDM_ERR_SHAPE, "gemm: rowvec must be 16 B aligned with ldrv %% 4 == 0");
   if (p->act != 0 && p->act != 1) return fail(TTVDM_ERR_SHAPE, "gemm: unknown act %d", p->act);
+  if (p->gn_stats_out || p->row_sums_out) {
+    if (p->geglu || p->out_fp32 || p->N % 32 != 0)
+      return fail(TTVDM_ERR_SHAPE, "gemm: gn_stats_out / row_sums_out need a bf16, non-GEGLU output with N %% 32 == 0");
+    if (p->gn_stats_out) {
+      const long long unit = p->mode == TTVDM_A_CONV3X3 ? (long long)p->H * p->W : (p->mode == TTVDM_A_TCONV3 ? p->W : 1);
+      if (p->gn_rows_per_inst <= 0 || p->M % p->gn_rows_per_inst != 0 || p->gn_rows_per_inst % unit != 0)
+        return fail(TTVDM_ERR_SHAPE, "gemm: gn_rows_per_inst=%d must divide M=%d and be a multiple of one image / frame",
+                    p->gn_rows_per_inst, p->M);
+    }
+  }
+  if (p->ln_rowsums && (!p->ln_colsum || p->N % 32 != 0 || p->out_fp32 || (p->k1 + k2) % 32 != 0))
+    return fail(TTVDM_ERR_SHAPE, "gemm: LayerNorm fold needs ln_colsum, a bf16 output and N %% 32 == 0");
+  if (p->ln_rowsums && (p->prevec || p->ln_row_add) && (p->prevec_rows <= 0 || p->prevec_mod <= 0))
+    return fail(TTVDM_ERR_SHAPE, "gemm: prevec needs prevec_rows > 0 and prevec_mod > 0");
+  if (p->prevec && (p->ldpv % 4 != 0 || (reinterpret_cast<uintptr_t>(p->prevec) & 15)))
+    return fail(TTVDM_ERR_SHAPE, "gemm: prevec must be 16 B aligned with ldpv %% 4 == 0");
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -717,7 +1028,9 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     static const int force_direct = getenv("TTVDM_DIRECT_EPILOGUE") != nullptr;  // A/B switch for profiling only
     if (force_direct) g.tma_epi = 0;
   }
-  const int epi_bytes = g.tma_epi ? kEpiWarps * kEpiBufBytes : 0;
+  // CTA-level GroupNorm accumulators ([N / 2][2] floats) live behind the operand ring / staging / resident W tile
+  const int gn_bytes = p->gn_stats_out ? ((p->N * 4 + 127) & ~127) : 0;
+  const int epi_bytes = (g.tma_epi ? kEpiWarps * kEpiBufBytes : 0) + gn_bytes;
   // B-resident schedule for short-K, many-M-tile GEMMs (the K = 320 level-0 linears): re-streaming the W tile from L2 for
   // every 128 rows makes them L2->SM bandwidth bound; pinning one N tile per CTA cuts the operand traffic per tile from
   // (128 + BN) * K to 128 * K elements. Needs the W tile, the epilogue staging and >= 3 A stages in shared memory.
@@ -848,6 +1161,33 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   g.out = p->out;
   g.ldo = p->ldo;
   g.out_fp32 = p->out_fp32;
+  g.gn_stats = static_cast<double*>(p->gn_stats_out);
+  g.gn_rpi = p->gn_rows_per_inst > 0 ? p->gn_rows_per_inst : 1;
+  g.row_sums = p->row_sums_out;
+  g.ln_parts = (p->k1 + k2) / 32;
+  {
+    // contiguous tile ranges per CTA keep a CTA inside one or two group instances, so the shared-memory GroupNorm
+    // accumulators are flushed (fp64 atomics) a handful of times per CTA instead of once per tile
+    static const char* e = getenv("TTVDM_GEMM_CONTIG");  // 0 / 1 forces it for every launch (A/B switch), unset = with stats
+    g.contig = e ? (atoi(e) != 0) : (p->gn_stats_out != nullptr);
+  }
+  g.rs_addvec = p->row_sums_out ? p->rs_addvec : nullptr;
+  g.rs_add_rows = p->rs_add_rows > 0 ? p->rs_add_rows : 1;
+  g.rs_add_mod = p->rs_add_mod > 0 ? p->rs_add_mod : 1;
+  g.ld_rs_add = p->ld_rs_add > 0 ? p->ld_rs_add : p->N;
+  if (g.rs_addvec && (g.ld_rs_add % 2 != 0 || (reinterpret_cast<uintptr_t>(g.rs_addvec) & 7)))
+    return fail(TTVDM_ERR_SHAPE, "gemm: rs_addvec must be 8 B aligned with an even row stride");
+  g.ln_rowsums = p->ln_rowsums;
+  g.ln_colsum = p->ln_colsum;
+  g.ln_eps = p->ln_eps;
+  g.ln_inv_k = 1.0f / (float)(p->k1 + k2);
+  g.prevec = p->ln_rowsums ? p->prevec : nullptr;
+  g.ln_row_add = p->ln_rowsums ? p->ln_row_add : nullptr;
+  g.prevec_rows = p->prevec_rows;
+  g.prevec_mod = (p->ln_rowsums && (p->prevec || p->ln_row_add)) ? p->prevec_mod : 0;
+  g.ldpv = p->ldpv > 0 ? p->ldpv : p->N;
+  if (g.ln_rowsums && !g.tma_epi)
+    return fail(TTVDM_ERR_SHAPE, "gemm: LayerNorm fold needs the TMA epilogue (16 B aligned bf16 out / res1, N %% 64 == 0 or K <= 640)");
   // vector epilogue needs 16 B aligned rows; otherwise the scalar path is taken only for ragged columns
   if (!p->out_fp32 && ((p->ldo % 8) != 0 && p->N >= 32)) return fail(TTVDM_ERR_SHAPE, "gemm: ldo %% 8 != 0");
   if ((p->res1 && p->ldr1 % 8) || (p->res2 && p->ldr2 % 8)) return fail(TTVDM_ERR_SHAPE, "gemm: ldr %% 8 != 0");
@@ -889,6 +1229,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     const int pair_tiles = ((g.m_tiles + 1) / 2) * g.n_tiles;
     const int max_pairs = g_num_sms / 2;
     const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+    if (g.contig) g.tiles_per_cta = (pair_tiles + pairs - 1) / pairs;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kNumThreads);
@@ -912,6 +1253,11 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
       attr_set = true;
     }
     const int grid = g.b_resident ? g.ctas_per_n * g.n_tiles : (num_tiles < g_num_sms ? num_tiles : g_num_sms);
+    if (g.contig) {
+      const int per = g.b_resident ? g.ctas_per_n : grid;       // CTAs sharing the tile list
+      const int total = g.b_resident ? g.m_tiles : num_tiles;   // tiles in that list
+      g.tiles_per_cta = (total + per - 1) / per;
+    }
     gemm_kernel<1><<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
   }
   TTVDM_CHECK_LAUNCH("gemm_kernel");

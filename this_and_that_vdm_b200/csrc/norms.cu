@@ -22,9 +22,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 __global__ void __launch_bounds__(512)
-gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double* __restrict__ sums) {
+gn_stats_kernel(GnSrc s1, GnSrc s2, int C, int rows_per_inst, int rows_per_cta, double* __restrict__ sums) {
   __shared__ double bins[64];  // fp64: the order of the atomics then only matters below ~1e-16 relative
-  const int C = s1.c + s2.c;
   const int cpg = C / 32;
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
@@ -91,16 +90,42 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, double*
   for (int i = threadIdx.x; i < 64; i += blockDim.x) atomicAdd(&sums[inst * 64 + i], bins[i]);
 }
 
+// `sums` (group sums of the sources that went through gn_stats_kernel; NULL if none did) plus, per source, the
+// per-(instance, channel pair) sums the producing GEMM's epilogue accumulated (ttvdm_gemm gn_stats_out) — folded into
+// the 32 group sums by every CTA (C / 2 <= 2560 doubles from L2: a few KB next to the >= 100 KB the CTA normalises).
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const double* __restrict__ sums,
+                const double* __restrict__ ps1, const double* __restrict__ ps2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                 __nv_bfloat16* __restrict__ out, int ldo) {
   __shared__ float s_mean[32], s_rstd[32];
+  __shared__ double s_bins[64];
   const int C = s1.c + s2.c;
   const int cpg = C / 32;
   const int inst = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(r0 + rows_per_cta, rows_per_inst);
+  if (ps1 != nullptr || ps2 != nullptr) {
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bins[i] = sums != nullptr ? sums[inst * 64 + i] : 0.0;
+    __syncthreads();
+    // pairs never straddle a group (cpg is even for every channel count of the path); host checks it
+    for (int pi = threadIdx.x; pi < (C >> 1); pi += blockDim.x) {
+      const int c = 2 * pi;
+      const double* src = nullptr;
+      if (c < s1.c) {
+        if (ps1 != nullptr) src = ps1 + ((size_t)inst * (s1.c >> 1) + pi) * 2;
+      } else if (ps2 != nullptr) {
+        src = ps2 + ((size_t)inst * (s2.c >> 1) + (pi - (s1.c >> 1))) * 2;
+      }
+      if (src != nullptr) {
+        const int gi = c / cpg;
+        atomicAdd(&s_bins[gi * 2], src[0]);
+        atomicAdd(&s_bins[gi * 2 + 1], src[1]);
+      }
+    }
+    __syncthreads();
+    sums = s_bins - inst * 64;  // same indexing below
+  }
   if (threadIdx.x < 32) {
     const double n = (double)rows_per_inst * cpg;
     const double m = sums[inst * 64 + threadIdx.x * 2] / n;
@@ -314,7 +339,9 @@ using namespace ttvdm;
 extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   if (int rc = ensure_init()) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!p || !p->x1 || !p->out || !p->stats || !p->gamma || !p->beta) return fail(TTVDM_ERR_SHAPE, "groupnorm: null");
+  if (!p || !p->x1 || !p->out || !p->gamma || !p->beta) return fail(TTVDM_ERR_SHAPE, "groupnorm: null");
+  if (!p->stats && (!p->pstats1 || (p->x2 && p->c2 && !p->pstats2)))
+    return fail(TTVDM_ERR_SHAPE, "groupnorm: stats workspace is required unless every source has producer statistics");
   const int c2 = p->x2 ? p->c2 : 0;
   const int C = p->c1 + c2;
   if (C % 32 != 0 || p->c1 % 8 != 0 || c2 % 8 != 0 || p->c1 > 4096 || c2 > 4096)
@@ -337,8 +364,16 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   int rows_per_cta = granule * steps;
   if (rows_per_cta > p->rows_per_inst) rows_per_cta = p->rows_per_inst;
   const int chunks = (p->rows_per_inst + rows_per_cta - 1) / rows_per_cta;
-  cudaError_t e = cudaMemsetAsync(p->stats, 0, (size_t)n_inst * 64 * sizeof(double), stream);
-  if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "groupnorm: memset: %s", cudaGetErrorString(e));
+  const double* ps1 = static_cast<const double*>(p->pstats1);
+  const double* ps2 = c2 ? static_cast<const double*>(p->pstats2) : nullptr;
+  if ((ps1 || ps2) && (C / 32) % 2 != 0)
+    return fail(TTVDM_ERR_SHAPE, "groupnorm: producer statistics need an even number of channels per group (C=%d)", C);
+  // sources whose statistics came out of the producing GEMM's epilogue are not read by the statistics pass
+  const bool need_pass = !ps1 || (c2 && !ps2);
+  if (need_pass) {
+    cudaError_t e = cudaMemsetAsync(p->stats, 0, (size_t)n_inst * 64 * sizeof(double), stream);
+    if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "groupnorm: memset: %s", cudaGetErrorString(e));
+  }
   const int vmax = (p->c1 > c2 ? p->c1 : c2) / 8;
   int threads = 512;
   if (vmax > threads) return fail(TTVDM_ERR_SHAPE, "groupnorm: more than 4096 channels per source");
@@ -347,10 +382,16 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
   dim3 grid(chunks, n_inst);
   GnSrc s1{static_cast<const __nv_bfloat16*>(p->x1), p->c1, p->ld1, 0};
   GnSrc s2{static_cast<const __nv_bfloat16*>(p->x2), c2, p->ld2, p->c1};
-  gn_stats_kernel<<<grid, threads, 0, stream>>>(s1, s2, p->rows_per_inst, rows_per_cta, static_cast<double*>(p->stats));
-  TTVDM_CHECK_LAUNCH("gn_stats_kernel");
+  if (need_pass) {
+    GnSrc t1 = s1, t2 = s2;
+    if (ps1) t1.c = 0;  // skipped by the kernel (c == 0); c_off of the other source is unaffected
+    if (ps2) t2.c = 0;
+    gn_stats_kernel<<<grid, threads, 0, stream>>>(t1, t2, C, p->rows_per_inst, rows_per_cta, static_cast<double*>(p->stats));
+    TTVDM_CHECK_LAUNCH("gn_stats_kernel");
+  }
   gn_apply_kernel<<<grid, threads, 0, stream>>>(s1, s2, p->rows_per_inst, rows_per_cta,
-                                                static_cast<const double*>(p->stats), p->gamma, p->beta, p->eps, p->silu,
+                                                need_pass ? static_cast<const double*>(p->stats) : nullptr, ps1, ps2,
+                                                p->gamma, p->beta, p->eps, p->silu,
                                                 static_cast<__nv_bfloat16*>(p->out), p->ldo);
   TTVDM_CHECK_LAUNCH("gn_apply_kernel");
   return 0;

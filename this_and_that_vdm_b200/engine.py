@@ -27,35 +27,44 @@ BF16 = torch.bfloat16
 PAD_IN = 64  # conv_in channels padded to one 64-wide K chunk
 
 
+def _src(t: torch.Tensor, dev) -> torch.Tensor:
+    """Parameter as the repack kernels read it: on the device, contiguous, in its own dtype (fp32 / fp16 / bf16)."""
+    t = t.detach()
+    if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        t = t.float()
+    return t.to(device=dev).contiguous()
+
+
 def _bf(t: torch.Tensor, dev) -> torch.Tensor:
-    return t.detach().to(device=dev, dtype=BF16).contiguous()
+    """-> bf16 through ttvdm_pack_linear (plain cast, no fold): [N, ...] becomes [N, K]; vectors keep their shape."""
+    t = _src(t, dev)
+    src = t.reshape(1, -1) if t.ndim < 2 else t.reshape(t.shape[0], -1)
+    out = torch.empty(src.shape, dtype=BF16, device=dev)
+    lib.pack_linear(src, out)
+    return out.view(t.shape) if t.ndim < 2 else out
 
 
 def _f32(t: torch.Tensor, dev) -> torch.Tensor:
-    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    t = _src(t, dev)
+    out = torch.empty(t.shape, dtype=torch.float32, device=dev)
+    lib.pack_vector(t, out)
+    return out
 
 
-def _pack_conv3x3(w: torch.Tensor, dev, pad_cin: int = 0) -> torch.Tensor:
-    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin'] tap-major then channel (Cin' = Cin zero-padded to pad_cin)."""
+def _pack_conv(w: torch.Tensor, dev, pad_cin: int = 0) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> [Cout, 9*Cin'] / [C, C, 3, 1, 1] -> [C, 3*C]: tap-major then channel (Cin' = Cin zero-padded
+    to pad_cin), bf16 — ttvdm_pack_conv_weight."""
+    w = _src(w, dev)
     cout, cin = w.shape[:2]
-    w = w.detach().permute(0, 2, 3, 1)  # [Cout, 3, 3, Cin]
-    if pad_cin and pad_cin > cin:
-        w = torch.nn.functional.pad(w, (0, pad_cin - cin))
-    return _bf(w.reshape(cout, -1), dev)
+    taps = w[0, 0].numel()
+    cp = max(pad_cin, cin)
+    out = torch.empty(cout, taps * cp, dtype=BF16, device=dev)
+    lib.pack_conv_weight(w, out, cin_pad=cp)
+    return out
 
 
-def _pack_tconv(w: torch.Tensor, dev) -> torch.Tensor:
-    """Conv3d (3,1,1) weight [C, C, 3, 1, 1] -> [C, 3*C] tap-major."""
-    cout, cin = w.shape[:2]
-    return _bf(w.detach().reshape(cout, cin, 3).permute(0, 2, 1).reshape(cout, 3 * cin), dev)
-
-
-def _pack_geglu(w: torch.Tensor, b: torch.Tensor, dev) -> Tuple[torch.Tensor, torch.Tensor]:
-    """GEGLU proj [8C, C]: rows [0,4C) hidden, [4C,8C) gate -> interleaved (hidden_j, gate_j)."""
-    n2 = w.shape[0] // 2
-    wi = torch.stack([w[:n2], w[n2:]], dim=1).reshape(w.shape[0], w.shape[1])
-    bi = torch.stack([b[:n2], b[n2:]], dim=1).reshape(-1)
-    return _bf(wi, dev), _f32(bi, dev)
+_pack_conv3x3 = _pack_conv
+_pack_tconv = _pack_conv
 
 
 @dataclass
@@ -88,8 +97,13 @@ class ResW:
 
 @dataclass
 class AttnW:
-    wqkv: Optional[torch.Tensor] = None  # self-attn fused [3C, C]
-    wq: Optional[torch.Tensor] = None    # cross-attn query [C, C]
+    """Attention projections. The LayerNorm in front of to_q/k/v is FOLDED into the packed weights: W' = W diag(gamma)
+    (bf16), bias' = W beta (fp32), colsum[n] = sum_k W'[n, k] (fp32, of the rounded W') — the GEMM epilogue then applies
+    rstd * (acc - mean * colsum) + bias' from the producer's row sums (include/ttvdm.h, ln_rowsums)."""
+    wqkv: Optional[torch.Tensor] = None  # self-attn fused [3C, C], LN-folded
+    wq: Optional[torch.Tensor] = None    # cross-attn query [C, C], LN-folded
+    w_b: Optional[torch.Tensor] = None   # folded bias of wqkv / wq
+    w_cs: Optional[torch.Tensor] = None  # column sums of wqkv / wq
     wk: Optional[torch.Tensor] = None    # cross-attn [C, 1024]
     wv: Optional[torch.Tensor] = None
     wo: torch.Tensor = None
@@ -98,10 +112,23 @@ class AttnW:
 
 @dataclass
 class FFW:
-    w1: torch.Tensor = None
-    b1: torch.Tensor = None
+    w1: torch.Tensor = None   # GEGLU proj, (hidden, gate) rows interleaved, LN-folded
+    b1: torch.Tensor = None   # folded bias
+    cs1: torch.Tensor = None  # column sums of w1
     w2: torch.Tensor = None
     b2: torch.Tensor = None
+
+
+@dataclass
+class TfLayer:
+    s_attn1: AttnW = None
+    s_attn2: AttnW = None
+    s_ff: FFW = None
+    t_ff_in: FFW = None
+    t_attn1: AttnW = None
+    t_attn2: AttnW = None
+    t_ff: FFW = None
+    pos_prevec: torch.Tensor = None  # fp32 [F, 8C]: frame positional embedding pushed through t_ff_in.w1 (input independent)
 
 
 @dataclass
@@ -112,14 +139,7 @@ class TfW:
     gn_b: torch.Tensor = None
     w_in: torch.Tensor = None
     b_in: torch.Tensor = None
-    ln: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = field(default_factory=dict)
-    s_attn1: AttnW = None
-    s_attn2: AttnW = None
-    s_ff: FFW = None
-    t_ff_in: FFW = None
-    t_attn1: AttnW = None
-    t_attn2: AttnW = None
-    t_ff: FFW = None
+    layers: List[TfLayer] = field(default_factory=list)
     pos_emb: torch.Tensor = None  # fp32 [F, C], input independent
     alpha: float = 0.5
     w_out: torch.Tensor = None
@@ -128,6 +148,28 @@ class TfW:
     pos_b1: torch.Tensor = None
     pos_w2: torch.Tensor = None
     pos_b2: torch.Tensor = None
+
+
+def _fold_ln(ws: Sequence[torch.Tensor], b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, dev,
+             geglu: bool = False):
+    """LayerNorm(gamma, beta) followed by Linear(cat(ws), b)  ->  (W' bf16, bias' fp32, colsum fp32) with
+    Linear(LN(x)) = rstd * (x W'^T - mean * colsum) + bias'   (ttvdm_pack_linear; geglu: (hidden_j, gate_j) row interleave)."""
+    ws = [_src(w, dev) for w in ws]
+    gamma, beta = _src(gamma, dev).to(ws[0].dtype), _src(beta, dev).to(ws[0].dtype)
+    N, K = sum(w.shape[0] for w in ws), ws[0].shape[1]
+    wf = torch.empty(N, K, dtype=BF16, device=dev)
+    bias = torch.empty(N, dtype=torch.float32, device=dev)
+    cs = torch.empty(N, dtype=torch.float32, device=dev)
+    row0 = 0
+    for w in ws:
+        lib.pack_linear(w, wf, bias=None if b is None else _src(b, dev).to(w.dtype), gamma=gamma, beta=beta, out_bias=bias,
+                        out_colsum=cs, geglu=geglu, out_row0=row0)
+        row0 += w.shape[0]
+    return wf, bias, cs
+
+
+def _sigmoid_scalar(t: torch.Tensor) -> float:
+    return 1.0 / (1.0 + math.exp(-float(t.detach().float().cpu().reshape(-1)[0])))
 
 
 class DenoiserEngine:
@@ -149,6 +191,13 @@ class DenoiserEngine:
         self.temb_dim = self.chans[0] * 4
         self.add_dim = cfg.addition_time_embed_dim
         self._pos_cache: Dict[int, bool] = {}
+        self._pos_rep: Dict[Tuple[int, int, int], torch.Tensor] = {}
+        # statistics pool: every GroupNorm / LayerNorm sum a GEMM epilogue accumulates during one forward lives here and
+        # is zeroed by ONE memset at the start of the forward (begin_step)
+        self._pool: Optional[torch.Tensor] = None
+        self._pool_used = 0
+        self._pool_high = 0
+        self.fuse_norm_stats = True  # False: standalone GroupNorm statistics pass (A/B switch for profiling / tests)
         self._pack(model)
 
     # ============================================================================================ packing
@@ -168,13 +217,13 @@ class DenoiserEngine:
             r.n2_g, r.n2_b = _f32(g(sp + ".norm2.weight"), dev), _f32(g(sp + ".norm2.bias"), dev)
             r.w2, r.b2 = _pack_conv3x3(g(sp + ".conv2.weight"), dev), _f32(g(sp + ".conv2.bias"), dev)
             if (sp + ".conv_shortcut.weight") in sd:
-                r.wsc = _bf(g(sp + ".conv_shortcut.weight").reshape(cout, cin), dev)
+                r.wsc = _bf(g(sp + ".conv_shortcut.weight"), dev)
                 r.bsc = _f32(g(sp + ".conv_shortcut.bias"), dev)
             r.tn1_g, r.tn1_b = _f32(g(tp + ".norm1.weight"), dev), _f32(g(tp + ".norm1.bias"), dev)
             r.tw1, r.tb1 = _pack_tconv(g(tp + ".conv1.weight"), dev), _f32(g(tp + ".conv1.bias"), dev)
             r.tn2_g, r.tn2_b = _f32(g(tp + ".norm2.weight"), dev), _f32(g(tp + ".norm2.bias"), dev)
             r.tw2, r.tb2 = _pack_tconv(g(tp + ".conv2.weight"), dev), _f32(g(tp + ".conv2.bias"), dev)
-            r.alpha = float(torch.sigmoid(g(prefix + ".time_mixer.mix_factor").float()).item())
+            r.alpha = _sigmoid_scalar(g(prefix + ".time_mixer.mix_factor"))
             # all time_emb_proj layers are fused into ONE [sum C, 1280] GEMM per forward (K13 hoist)
             r.temb_off_s = self.temb_cols
             temb_w.append(g(sp + ".time_emb_proj.weight")); temb_b.append(g(sp + ".time_emb_proj.bias"))
@@ -184,40 +233,46 @@ class DenoiserEngine:
             self.temb_cols += cout
             return r
 
-        def attn(prefix: str, cross: bool) -> AttnW:
+        def attn(prefix: str, cross: bool, ln: str) -> AttnW:
             a = AttnW()
+            gamma, beta = g(ln + ".weight"), g(ln + ".bias")
             if cross:
-                a.wq = _bf(g(prefix + ".to_q.weight"), dev)
+                a.wq, a.w_b, a.w_cs = _fold_ln([g(prefix + ".to_q.weight")], None, gamma, beta, dev)
                 a.wk = _bf(g(prefix + ".to_k.weight"), dev)
                 a.wv = _bf(g(prefix + ".to_v.weight"), dev)
             else:
-                a.wqkv = _bf(torch.cat([g(prefix + ".to_q.weight"), g(prefix + ".to_k.weight"),
-                                        g(prefix + ".to_v.weight")], 0), dev)
+                a.wqkv, a.w_b, a.w_cs = _fold_ln([g(prefix + ".to_q.weight"), g(prefix + ".to_k.weight"),
+                                                  g(prefix + ".to_v.weight")], None, gamma, beta, dev)
             a.wo, a.bo = _bf(g(prefix + ".to_out.0.weight"), dev), _f32(g(prefix + ".to_out.0.bias"), dev)
             return a
 
-        def ff(prefix: str) -> FFW:
+        def ff(prefix: str, ln: str) -> FFW:
             f = FFW()
-            f.w1, f.b1 = _pack_geglu(g(prefix + ".net.0.proj.weight"), g(prefix + ".net.0.proj.bias"), dev)
+            # GEGLU rows interleaved (hidden_j, gate_j) by the repack kernel: weights, bias and column sums stay aligned
+            f.w1, f.b1, f.cs1 = _fold_ln([g(prefix + ".net.0.proj.weight")], g(prefix + ".net.0.proj.bias"),
+                                         g(ln + ".weight"), g(ln + ".bias"), dev, geglu=True)
             f.w2, f.b2 = _bf(g(prefix + ".net.2.weight"), dev), _f32(g(prefix + ".net.2.bias"), dev)
             return f
 
         def tf(prefix: str, heads: int) -> TfW:
             C = g(prefix + ".proj_in.weight").shape[0]
             t = TfW(C=C, heads=heads)
-            if (prefix + ".transformer_blocks.1.norm1.weight") in sd:
-                raise lib.TtvdmError("transformer_layers_per_block > 1 is not supported by the sm_100a engine")
             t.gn_g, t.gn_b = _f32(g(prefix + ".norm.weight"), dev), _f32(g(prefix + ".norm.bias"), dev)
             t.w_in, t.b_in = _bf(g(prefix + ".proj_in.weight"), dev), _f32(g(prefix + ".proj_in.bias"), dev)
-            sb, tb = prefix + ".transformer_blocks.0", prefix + ".temporal_transformer_blocks.0"
-            for name, p in [("s1", sb + ".norm1"), ("s2", sb + ".norm2"), ("s3", sb + ".norm3"),
-                            ("tin", tb + ".norm_in"), ("t1", tb + ".norm1"), ("t2", tb + ".norm2"),
-                            ("t3", tb + ".norm3")]:
-                t.ln[name] = (_f32(g(p + ".weight"), dev), _f32(g(p + ".bias"), dev))
-            t.s_attn1, t.s_attn2, t.s_ff = attn(sb + ".attn1", False), attn(sb + ".attn2", True), ff(sb + ".ff")
-            t.t_ff_in, t.t_attn1 = ff(tb + ".ff_in"), attn(tb + ".attn1", False)
-            t.t_attn2, t.t_ff = attn(tb + ".attn2", True), ff(tb + ".ff")
-            t.alpha = float(torch.sigmoid(g(prefix + ".time_mixer.mix_factor").float()).item())
+            i = 0
+            while (prefix + f".transformer_blocks.{i}.norm1.weight") in sd:  # transformer_layers_per_block >= 1
+                sb, tb = prefix + f".transformer_blocks.{i}", prefix + f".temporal_transformer_blocks.{i}"
+                L = TfLayer()
+                L.s_attn1 = attn(sb + ".attn1", False, sb + ".norm1")
+                L.s_attn2 = attn(sb + ".attn2", True, sb + ".norm2")
+                L.s_ff = ff(sb + ".ff", sb + ".norm3")
+                L.t_ff_in = ff(tb + ".ff_in", tb + ".norm_in")
+                L.t_attn1 = attn(tb + ".attn1", False, tb + ".norm1")
+                L.t_attn2 = attn(tb + ".attn2", True, tb + ".norm2")
+                L.t_ff = ff(tb + ".ff", tb + ".norm3")
+                t.layers.append(L)
+                i += 1
+            t.alpha = _sigmoid_scalar(g(prefix + ".time_mixer.mix_factor"))
             t.w_out, t.b_out = _bf(g(prefix + ".proj_out.weight"), dev), _f32(g(prefix + ".proj_out.bias"), dev)
             pe = prefix + ".time_pos_embed"
             t.pos_w1, t.pos_b1 = _bf(g(pe + ".linear_1.weight"), dev), _f32(g(pe + ".linear_1.bias"), dev)
@@ -279,15 +334,20 @@ class DenoiserEngine:
             i = 0
             while f"controlnet_down_blocks.{i}.weight" in sd:
                 w = g(f"controlnet_down_blocks.{i}.weight")
-                self.zero_w.append(_bf(w.reshape(w.shape[0], w.shape[1]), dev))
+                self.zero_w.append(_bf(w, dev))
                 self.zero_b.append(_f32(g(f"controlnet_down_blocks.{i}.bias"), dev))
                 i += 1
             w = g("controlnet_mid_block.weight")
-            self.zero_mid_w = _bf(w.reshape(w.shape[0], w.shape[1]), dev)
+            self.zero_mid_w = _bf(w, dev)
             self.zero_mid_b = _f32(g("controlnet_mid_block.bias"), dev)
         # ---- fused time_emb_proj
-        self.temb_w = _bf(torch.cat(temb_w, 0), dev)
-        self.temb_b = _f32(torch.cat(temb_b, 0), dev)
+        self.temb_w = torch.empty(self.temb_cols, temb_w[0].shape[1], dtype=BF16, device=dev)
+        self.temb_b = torch.empty(self.temb_cols, dtype=torch.float32, device=dev)
+        row0 = 0
+        for w, b in zip(temb_w, temb_b):
+            lib.pack_linear(_src(w, dev), self.temb_w, out_row0=row0)
+            lib.pack_vector(_src(b, dev), self.temb_b[row0:row0 + w.shape[0]])
+            row0 += w.shape[0]
 
     def all_transformers(self) -> List[TfW]:
         out = []
@@ -302,37 +362,102 @@ class DenoiserEngine:
     def _empty(self, *shape, dtype=BF16) -> torch.Tensor:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
+    # ---- statistics pool
+    def begin_step(self) -> None:
+        """Zero the statistics pool (one memset) and rewind it. Called once per network forward."""
+        need = self._pool_high
+        if self._pool is None or need > self._pool.numel():
+            self._pool = torch.zeros(max(need + (need >> 2), 1 << 20), dtype=torch.uint8, device=self.device)
+        else:
+            self._pool[: max(need, 16)].zero_()
+        self._pool_used = 0
+
+    def _stat(self, numel: int, dtype) -> torch.Tensor:
+        """`numel` zeroed elements of the step's statistics pool (falls back to a fresh zero tensor while the pool's
+        size is still being learned: first forward of a new shape)."""
+        nbytes = numel * (8 if dtype == torch.float64 else 4)
+        off = (self._pool_used + 15) & ~15
+        self._pool_used = off + nbytes
+        self._pool_high = max(self._pool_high, self._pool_used)
+        if self._pool is None or self._pool_used > self._pool.numel():
+            return torch.zeros(numel, dtype=dtype, device=self.device)
+        return self._pool[off:off + nbytes].view(dtype)
+
+    def _norm_out_kw(self, out: torch.Tensor, M: int, N: int, gn_rpi: int, ln_out: bool, rs_add) -> dict:
+        """Epilogue statistics requests for a GEMM that writes `out` [M, N]: GroupNorm pair sums for a consumer whose
+        group instance spans gn_rpi rows, and / or LayerNorm row sums. The buffers ride on the tensor object."""
+        kw = {}
+        out.gn_stats = None
+        out.ln_sums = None
+        if gn_rpi and self.fuse_norm_stats and N % 64 == 0 and M % gn_rpi == 0:
+            st = self._stat((M // gn_rpi) * N, torch.float64)
+            kw.update(gn_stats_out=st, gn_rows_per_inst=gn_rpi)
+            out.gn_stats = (st, gn_rpi)
+        if ln_out:
+            # [N / 32, M, 2] partial sums: one writer per slot, so plain (un-zeroed) scratch is enough
+            rs = self._empty((N // 32) * M * 2, dtype=torch.float32)
+            kw.update(row_sums_out=rs)
+            if rs_add is not None:
+                kw.update(rs_addvec=rs_add[0], rs_add_rows=rs_add[1], rs_add_mod=rs_add[2])
+            out.ln_sums = rs
+        return kw
+
     def _linear(self, a, w, *, M, bias=None, out=None, res1=None, s1=1.0, res2=None, s2=1.0, s0=1.0, geglu=False,
-                a2=None, k2=0, act=0, out_fp32=False, lda=None):
+                a2=None, k2=0, act=0, out_fp32=False, lda=None, rowvec=None, rows_per_vec=0, ldrv=0, gn_rpi=0,
+                ln_out=False, rs_add=None, ln=None, prevec=None):
+        """ln = (row sums of `a`, column sums of `w`): `a` is the UN-normalised tensor and `w` carries the folded
+        LayerNorm gain. prevec = (table [mod, N], rows, mod)."""
         N, K = w.shape[0], w.shape[1] - k2
         if out is None:
             out = self._empty(M, N // 2 if geglu else N, dtype=torch.float32 if out_fp32 else BF16)
+        kw = self._norm_out_kw(out, M, N, gn_rpi, ln_out, rs_add) if not (geglu or out_fp32) else {}
+        if ln is not None:
+            kw.update(ln_rowsums=ln[0], ln_colsum=ln[1], ln_eps=1e-5)
+            if prevec is not None:
+                kw.update(prevec=prevec[0], prevec_rows=prevec[1], prevec_mod=prevec[2], ldpv=N)
         lib.gemm(a, w, out, M=M, N=N, k1=K, a2=a2, k2=k2, bias=bias, res1=res1, s1=s1, res2=res2, s2=s2, s0=s0,
-                 geglu=geglu, act=act, out_fp32=out_fp32, lda=lda)
+                 geglu=geglu, act=act, out_fp32=out_fp32, lda=lda, rowvec=rowvec, rows_per_vec=rows_per_vec, ldrv=ldrv,
+                 **kw)
         return out
 
     def _conv3(self, x, w, bias, *, n_img, H, W, cin, out=None, rowvec=None, rows_per_vec=0, ldrv=0, res1=None,
-               out_fp32=False):
+               out_fp32=False, gn_rpi=0):
         N = w.shape[0]
         M = n_img * H * W
         if out is None:
             out = self._empty(M, N, dtype=torch.float32 if out_fp32 else BF16)
+        kw = self._norm_out_kw(out, M, N, gn_rpi, False, None) if not out_fp32 else {}
         lib.gemm(x, w, out, M=M, N=N, k1=cin, mode=lib.A_CONV3X3, n_img=n_img, H=H, W=W, bias=bias, rowvec=rowvec,
-                 rows_per_vec=rows_per_vec, ldrv=ldrv, res1=res1, out_fp32=out_fp32)
+                 rows_per_vec=rows_per_vec, ldrv=ldrv, res1=res1, out_fp32=out_fp32, **kw)
+        return out
+
+    def _tconv(self, x, w, bias, *, B, F, S, C, out=None, rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None,
+               s1=1.0, res2=None, s2=1.0, gn_rpi=0):
+        M = B * F * S
+        if out is None:
+            out = self._empty(M, C)
+        kw = self._norm_out_kw(out, M, C, gn_rpi, False, None)
+        lib.gemm(x, w, out, M=M, N=C, k1=C, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=bias, rowvec=rowvec,
+                 rows_per_vec=rows_per_vec, ldrv=ldrv, s0=s0, res1=res1, s1=s1, res2=res2, s2=s2, **kw)
         return out
 
     def _gn(self, x, gamma, beta, *, rows, rows_per_inst, eps, silu, x2=None):
+        """GroupNorm(32) (+SiLU, + channel concat with x2). Sources whose producing GEMM left per-pair sums for this
+        instance size (tensor.gn_stats) skip the statistics pass."""
         c1 = x.shape[1]
         c2 = x2.shape[1] if x2 is not None else 0
         out = self._empty(rows, c1 + c2)
-        stats = self._empty((rows // rows_per_inst) * 64, dtype=torch.float64)
-        lib.groupnorm(x, out, stats, gamma, beta, c1=c1, rows=rows, rows_per_inst=rows_per_inst, eps=eps, silu=silu,
-                      x2=x2, c2=c2)
-        return out
 
-    def _ln(self, x, gb, *, rows, C, addvec=None, F=0, S=0, sum_out=None):
-        out = self._empty(rows, C)
-        lib.layernorm(x, out, gb[0], gb[1], rows=rows, C=C, addvec=addvec, F=F, S=S, sum_out=sum_out)
+        def pst(t):
+            st = getattr(t, "gn_stats", None) if t is not None else None
+            return st[0] if (st is not None and st[1] == rows_per_inst and ((c1 + c2) // 32) % 2 == 0) else None
+
+        ps1, ps2 = pst(x), pst(x2)
+        stats = None
+        if ps1 is None or (x2 is not None and ps2 is None):
+            stats = self._empty((rows // rows_per_inst) * 64, dtype=torch.float64)
+        lib.groupnorm(x, out, stats, gamma, beta, c1=c1, rows=rows, rows_per_inst=rows_per_inst, eps=eps, silu=silu,
+                      x2=x2, c2=c2, pstats1=ps1, pstats2=ps2)
         return out
 
     # ============================================================================================ embeddings
@@ -354,24 +479,28 @@ class DenoiserEngine:
         semb = self._linear(h2, self.ae_w2, M=R, bias=self.ae_b2, res1=emb, act=1)
         return self._linear(semb, self.temb_w, M=R, bias=self.temb_b, out_fp32=True)
 
-    def context_kv(self, ehs: torch.Tensor) -> List[Tuple[torch.Tensor, ...]]:
-        """Cross-attention K/V of the (constant) context for every transformer: computed once per video instead of
+    def context_kv(self, ehs: torch.Tensor) -> List[List[Tuple[torch.Tensor, ...]]]:
+        """Cross-attention K/V of the (constant) context for every transformer layer: computed once per video instead of
         per frame / per pixel (reference: svd/unet_spatio_temporal_condition.py:452 repeat_interleave,
-        svd/diffusion_arch/transformer_temporal.py:316-319 broadcast). ehs [B, L, D] -> per transformer
+        svd/diffusion_arch/transformer_temporal.py:316-319 broadcast). ehs [B, L, D] -> per transformer, per layer
         (k_s, v_s, k_t, v_t), each bf16 [B, L, C]."""
         B, L, D = ehs.shape
         x = _bf(ehs.reshape(B * L, D), self.device)
         out = []
         for t in self.all_transformers():
-            ks = self._linear(x, t.s_attn2.wk, M=B * L)
-            vs = self._linear(x, t.s_attn2.wv, M=B * L)
-            kt = self._linear(x, t.t_attn2.wk, M=B * L)
-            vt = self._linear(x, t.t_attn2.wv, M=B * L)
-            out.append((ks, vs, kt, vt))
+            per_layer = []
+            for ly in t.layers:
+                ks = self._linear(x, ly.s_attn2.wk, M=B * L)
+                vs = self._linear(x, ly.s_attn2.wv, M=B * L)
+                kt = self._linear(x, ly.t_attn2.wk, M=B * L)
+                vt = self._linear(x, ly.t_attn2.wv, M=B * L)
+                per_layer.append((ks, vs, kt, vt))
+            out.append(per_layer)
         return out
 
     def _ensure_pos_emb(self, F: int) -> None:
-        """time_pos_embed(time_proj(arange(F))) is input independent (transformer_temporal.py:328-339): once."""
+        """time_pos_embed(time_proj(arange(F))) is input independent (transformer_temporal.py:328-339): once. So is its
+        image under the (LayerNorm-folded) ff_in projection, which the GEGLU GEMM adds before the LayerNorm scale."""
         if F in self._pos_cache:
             return
         frames = torch.arange(F, device=self.device, dtype=torch.float32)
@@ -380,19 +509,32 @@ class DenoiserEngine:
             lib.sinusoid(frames, ts, n=F, dim=t.C)
             h = self._linear(ts, t.pos_w1, M=F, bias=t.pos_b1, act=1)
             t.pos_emb = self._linear(h, t.pos_w2, M=F, bias=t.pos_b2, out_fp32=True)
-        self._pos_cache[F] = True
+            pe = _bf(t.pos_emb, self.device)
+            for ly in t.layers:
+                ly.pos_prevec = self._linear(pe, ly.t_ff_in.w1, M=F, out_fp32=True)
+        self._pos_cache = {F: True}
+        self._pos_rep = {}
+
+    def _pos_table(self, t: TfW, B: int, F: int) -> torch.Tensor:
+        """fp32 [B*F, C]: the frame positional embedding as a per-(batch, frame) row vector (rowvec index = row / S)."""
+        key = (id(t), B, F)
+        if key not in self._pos_rep:
+            self._pos_rep[key] = t.pos_emb.repeat(B, 1).contiguous()
+        return self._pos_rep[key]
 
     # ============================================================================================ blocks
     def _resblock(self, r: ResW, x, skip, *, B, F, H, W, temb, out=None, out_res2=None, out_s2=0.0):
         """SpatioTemporalResBlock (diffusers; A.3-A.6). x [rows, c], skip optional second source (channel concat).
-        temb fp32 [B, sum C]. Returns [rows, cout]."""
+        temb fp32 [B, sum C]. Returns [rows, cout] carrying per-frame GroupNorm sums for its consumer.
+        Every GroupNorm here reads statistics that the producing GEMM's epilogue accumulated (gn_rpi = rows per group
+        instance of the CONSUMER: S for the 4-D norms, F*S for the 5-D temporal ones); only the apply pass remains."""
         S = H * W
         rows = B * F * S
         n_img = B * F
         ldrv = self.temb_cols
         y = self._gn(x, r.n1_g, r.n1_b, rows=rows, rows_per_inst=S, eps=r.eps, silu=True, x2=skip)
         h = self._conv3(y, r.w1, r.b1, n_img=n_img, H=H, W=W, cin=r.cin, rowvec=temb[:, r.temb_off_s:],
-                        rows_per_vec=F * S, ldrv=ldrv)
+                        rows_per_vec=F * S, ldrv=ldrv, gn_rpi=S)
         y = self._gn(h, r.n2_g, r.n2_b, rows=rows, rows_per_inst=S, eps=r.eps, silu=True)
         if r.wsc is not None:
             if skip is not None:
@@ -401,73 +543,75 @@ class DenoiserEngine:
                 sc = self._linear(x, r.wsc, M=rows, bias=r.bsc)
         else:
             sc = x
-        hs = self._conv3(y, r.w2, r.b2, n_img=n_img, H=H, W=W, cin=r.cout, res1=sc, out=h)
+        hs = self._conv3(y, r.w2, r.b2, n_img=n_img, H=H, W=W, cin=r.cout, res1=sc, out=h, gn_rpi=F * S)
         # temporal branch: 5-D GroupNorm (stats over all frames of a video) + 3-tap conv over frames
         y = self._gn(hs, r.tn1_g, r.tn1_b, rows=rows, rows_per_inst=F * S, eps=r.eps, silu=True)
-        t1 = self._empty(rows, r.cout)
-        lib.gemm(y, r.tw1, t1, M=rows, N=r.cout, k1=r.cout, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=r.tb1,
-                 rowvec=temb[:, r.temb_off_t:], rows_per_vec=F * S, ldrv=ldrv)
+        t1 = self._tconv(y, r.tw1, r.tb1, B=B, F=F, S=S, C=r.cout, rowvec=temb[:, r.temb_off_t:], rows_per_vec=F * S,
+                         ldrv=ldrv, gn_rpi=F * S)
         y = self._gn(t1, r.tn2_g, r.tn2_b, rows=rows, rows_per_inst=F * S, eps=r.eps, silu=True)
         # AlphaBlender: a*hs + (1-a)*(hs + conv) = hs + (1-a)*conv ; optional fused extra residual (ControlNet)
         if out is None:
             out = t1
-        lib.gemm(y, r.tw2, out, M=rows, N=r.cout, k1=r.cout, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=r.tb2,
-                 s0=1.0 - r.alpha, res1=hs, s1=1.0, res2=out_res2, s2=out_s2)
-        return out
+        return self._tconv(y, r.tw2, r.tb2, B=B, F=F, S=S, C=r.cout, out=out, s0=1.0 - r.alpha, res1=hs, s1=1.0,
+                           res2=out_res2, s2=out_s2, gn_rpi=S)
 
     def _transformer(self, t: TfW, x, kv, *, B, F, H, W, n_ctx, batch_offset):
-        """TransformerSpatioTemporalModel.forward (svd/diffusion_arch/transformer_temporal.py:276-381)."""
+        """TransformerSpatioTemporalModel.forward (svd/diffusion_arch/transformer_temporal.py:276-381).
+        No LayerNorm kernel runs: each of the 7 LayerNorms per layer is folded into the GEMM that consumes it (folded
+        weights + epilogue scale from the row sums the producing GEMM's epilogue accumulated), and `hidden + frame
+        positional embedding` (:356) is never materialised — the embedding enters the statistics (rs_add), the ff_in
+        projection (prevec) and the ff_in residual (rowvec) separately."""
         S = H * W
         rows = B * F * S
         C = t.C
-        ks, vs, kt, vt = kv
-        L = ks.shape[0] // n_ctx
         scale = 0.125
         y = self._gn(x, t.gn_g, t.gn_b, rows=rows, rows_per_inst=S, eps=1e-6, silu=False)
-        h = self._linear(y, t.w_in, M=rows, bias=t.b_in)
-        # ---- spatial BasicTransformerBlock
-        y = self._ln(h, t.ln["s1"], rows=rows, C=C)
-        qkv = self._linear(y, t.s_attn1.wqkv, M=rows)
-        o = y  # reuse
-        lib.attn_spatial(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, n_img=B * F,
-                         heads=t.heads, seq=S, scale=scale)
-        self._linear(o, t.s_attn1.wo, M=rows, bias=t.s_attn1.bo, res1=h, out=h)
-        y = self._ln(h, t.ln["s2"], rows=rows, C=C)
-        q = self._linear(y, t.s_attn2.wq, M=rows)
-        lib.attn_cross(q, ks, vs, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
-                       temporal=False, batch_offset=batch_offset, scale=scale)
-        self._linear(y, t.s_attn2.wo, M=rows, bias=t.s_attn2.bo, res1=h, out=h)
-        y = self._ln(h, t.ln["s3"], rows=rows, C=C)
-        gg = self._linear(y, t.s_ff.w1, M=rows, bias=t.s_ff.b1, geglu=True)
-        self._linear(gg, t.s_ff.w2, M=rows, bias=t.s_ff.b2, res1=h, out=h)  # h == x_spatial
-        # ---- TemporalBasicTransformerBlock on (h + frame positional embedding); rows stay (b, f, s)
-        hm = self._empty(rows, C)
-        y = self._ln(h, t.ln["tin"], rows=rows, C=C, addvec=t.pos_emb, F=F, S=S, sum_out=hm)
-        gg = self._linear(y, t.t_ff_in.w1, M=rows, bias=t.t_ff_in.b1, geglu=True, out=gg)
-        self._linear(gg, t.t_ff_in.w2, M=rows, bias=t.t_ff_in.b2, res1=hm, out=hm)
-        y = self._ln(hm, t.ln["t1"], rows=rows, C=C)
-        qkv = self._linear(y, t.t_attn1.wqkv, M=rows, out=qkv)
-        lib.attn_temporal(qkv, qkv[:, C:], qkv[:, 2 * C:], y, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, B=B, F=F, S=S,
-                          heads=t.heads, scale=scale)
-        self._linear(y, t.t_attn1.wo, M=rows, bias=t.t_attn1.bo, res1=hm, out=hm)
-        y = self._ln(hm, t.ln["t2"], rows=rows, C=C)
-        q = self._linear(y, t.t_attn2.wq, M=rows, out=q)
-        lib.attn_cross(q, kt, vt, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
-                       temporal=True, batch_offset=batch_offset, scale=scale)
-        self._linear(y, t.t_attn2.wo, M=rows, bias=t.t_attn2.bo, res1=hm, out=hm)
-        y = self._ln(hm, t.ln["t3"], rows=rows, C=C)
-        gg = self._linear(y, t.t_ff.w1, M=rows, bias=t.t_ff.b1, geglu=True, out=gg)
-        # AlphaBlender fused: a*h + (1-a)*(ff + hm)
-        a = t.alpha
-        self._linear(gg, t.t_ff.w2, M=rows, bias=t.t_ff.b2, s0=1.0 - a, res1=hm, s1=1.0 - a, res2=h, s2=a, out=h)
+        h = self._linear(y, t.w_in, M=rows, bias=t.b_in, ln_out=True)
+        o = y  # attention outputs reuse the normalised-input buffer
+        qkv = q = gg = hm = None
+        pos_rs = (t.pos_emb, S, F)
+        pos_tab = self._pos_table(t, B, F)
+        for li, (ly, (ks, vs, kt, vt)) in enumerate(zip(t.layers, kv)):
+            L = ks.shape[0] // n_ctx
+            last = li == len(t.layers) - 1
+            # ---- spatial BasicTransformerBlock
+            qkv = self._linear(h, ly.s_attn1.wqkv, M=rows, bias=ly.s_attn1.w_b, ln=(h.ln_sums, ly.s_attn1.w_cs), out=qkv)
+            lib.attn_spatial(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, n_img=B * F,
+                             heads=t.heads, seq=S, scale=scale)
+            self._linear(o, ly.s_attn1.wo, M=rows, bias=ly.s_attn1.bo, res1=h, out=h, ln_out=True)
+            q = self._linear(h, ly.s_attn2.wq, M=rows, bias=ly.s_attn2.w_b, ln=(h.ln_sums, ly.s_attn2.w_cs), out=q)
+            lib.attn_cross(q, ks, vs, o, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
+                           temporal=False, batch_offset=batch_offset, scale=scale)
+            self._linear(o, ly.s_attn2.wo, M=rows, bias=ly.s_attn2.bo, res1=h, out=h, ln_out=True)
+            gg = self._linear(h, ly.s_ff.w1, M=rows, bias=ly.s_ff.b1, geglu=True, ln=(h.ln_sums, ly.s_ff.cs1), out=gg)
+            # h == x_spatial; its row sums are taken over (h + frame positional embedding) for norm_in
+            self._linear(gg, ly.s_ff.w2, M=rows, bias=ly.s_ff.b2, res1=h, out=h, ln_out=True, rs_add=pos_rs)
+            # ---- TemporalBasicTransformerBlock on (h + pos); rows stay (b, f, s)
+            gg = self._linear(h, ly.t_ff_in.w1, M=rows, bias=ly.t_ff_in.b1, geglu=True, ln=(h.ln_sums, ly.t_ff_in.cs1),
+                              prevec=(ly.pos_prevec, S, F), out=gg)
+            hm = self._linear(gg, ly.t_ff_in.w2, M=rows, bias=ly.t_ff_in.b2, res1=h, rowvec=pos_tab, rows_per_vec=S,
+                              ldrv=C, out=hm, ln_out=True)
+            qkv = self._linear(hm, ly.t_attn1.wqkv, M=rows, bias=ly.t_attn1.w_b, ln=(hm.ln_sums, ly.t_attn1.w_cs), out=qkv)
+            lib.attn_temporal(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, B=B, F=F, S=S,
+                              heads=t.heads, scale=scale)
+            self._linear(o, ly.t_attn1.wo, M=rows, bias=ly.t_attn1.bo, res1=hm, out=hm, ln_out=True)
+            q = self._linear(hm, ly.t_attn2.wq, M=rows, bias=ly.t_attn2.w_b, ln=(hm.ln_sums, ly.t_attn2.w_cs), out=q)
+            lib.attn_cross(q, kt, vt, o, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
+                           temporal=True, batch_offset=batch_offset, scale=scale)
+            self._linear(o, ly.t_attn2.wo, M=rows, bias=ly.t_attn2.bo, res1=hm, out=hm, ln_out=True)
+            gg = self._linear(hm, ly.t_ff.w1, M=rows, bias=ly.t_ff.b1, geglu=True, ln=(hm.ln_sums, ly.t_ff.cs1), out=gg)
+            # AlphaBlender fused: a*h + (1-a)*(ff + hm); the next layer's norm1 needs the row sums of the blend
+            a = t.alpha
+            self._linear(gg, ly.t_ff.w2, M=rows, bias=ly.t_ff.b2, s0=1.0 - a, res1=hm, s1=1.0 - a, res2=h, s2=a, out=h,
+                         ln_out=not last)
         # ---- proj_out + input residual
-        return self._linear(h, t.w_out, M=rows, bias=t.b_out, res1=x, out=hm)
+        return self._linear(h, t.w_out, M=rows, bias=t.b_out, res1=x, out=hm, gn_rpi=S)
 
     # ============================================================================================ network halves
     def encode(self, x_in, temb, kvs, *, B, F, H, W, n_ctx, batch_offset):
         """conv_in + down blocks. Returns (x, skips[12], dims[12], ti) — shared by UNet and ControlNet."""
         n_img = B * F
-        x = self._conv3(x_in, self.conv_in_w, self.conv_in_b, n_img=n_img, H=H, W=W, cin=PAD_IN)
+        x = self._conv3(x_in, self.conv_in_w, self.conv_in_b, n_img=n_img, H=H, W=W, cin=PAD_IN, gn_rpi=H * W)
         skips, dims = [x], [(H, W)]
         ti = 0
         for blk in self.down:
@@ -484,7 +628,7 @@ class DenoiserEngine:
                 col = self._empty(n_img * (H // 2) * (W // 2), 9 * C)
                 lib.im2col_s2(x, col, n_img=n_img, H=H, W=W, C=C)
                 H, W = H // 2, W // 2
-                x = self._linear(col, blk["down_w"], M=n_img * H * W, bias=blk["down_b"])
+                x = self._linear(col, blk["down_w"], M=n_img * H * W, bias=blk["down_b"], gn_rpi=H * W)
                 skips.append(x)
                 dims.append((H, W))
         return x, skips, dims, ti
@@ -512,27 +656,29 @@ class DenoiserEngine:
                 up = self._empty(n_img * 4 * H * W, C)
                 lib.upsample2x(x, up, n_img=n_img, H=H, W=W, C=C)
                 H, W = 2 * H, 2 * W
-                x = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n_img, H=H, W=W, cin=C)
+                x = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n_img, H=H, W=W, cin=C, gn_rpi=H * W)
         rows = n_img * H * W
         y = self._gn(x, self.out_g, self.out_b, rows=rows, rows_per_inst=H * W, eps=1e-5, silu=True)
         return self._conv3(y, self.conv_out_w, self.conv_out_b, n_img=n_img, H=H, W=W, cin=x.shape[1], out_fp32=True)
 
     def zero_convs(self, skips, mid, scales: Sequence[float], into: Optional[Sequence[torch.Tensor]] = None,
-                   mid_into: Optional[torch.Tensor] = None):
+                   mid_into: Optional[torch.Tensor] = None, n_img: int = 0):
         """ControlNet 1x1 'zero' convs x conditioning scale (svd/temporal_controlnet.py:616-633). With `into`, the
         residual is accumulated straight into the UNet's skip tensors in the GEMM epilogue (U4 / K15)."""
         outs = []
         for i, s in enumerate(skips):
             rows = s.shape[0]
             if into is not None:
+                # the merged skip feeds an up-block GroupNorm: its per-frame sums come out of this epilogue
+                rpi = rows // n_img if n_img else 0
                 outs.append(self._linear(s, self.zero_w[i], M=rows, bias=self.zero_b[i], s0=scales[i], res1=into[i],
-                                         s1=1.0, out=into[i]))
+                                         s1=1.0, out=into[i], gn_rpi=rpi))
             else:
                 outs.append(self._linear(s, self.zero_w[i], M=rows, bias=self.zero_b[i], s0=scales[i]))
         rows = mid.shape[0]
         if mid_into is not None:
             m = self._linear(mid, self.zero_mid_w, M=rows, bias=self.zero_mid_b, s0=scales[-1], res1=mid_into, s1=1.0,
-                             out=mid_into)
+                             out=mid_into, gn_rpi=rows // n_img if n_img else 0)
         else:
             m = self._linear(mid, self.zero_mid_w, M=rows, bias=self.zero_mid_b, s0=scales[-1])
         return outs, m
@@ -576,6 +722,7 @@ class DenoiserEngine:
     def unet_forward(self, sample, timestep, ehs, added_time_ids, down_res=None, mid_res=None):
         assert self.kind == "unet"
         x_in, temb, kvs, (B, F, H, W) = self._prep_inputs(sample, timestep, ehs, added_time_ids)
+        self.begin_step()
         kw = dict(B=B, F=F, n_ctx=B, batch_offset=0)
         x, skips, dims, ti = self.encode(x_in, temb, kvs, H=H, W=W, **kw)
         hl, wl = dims[-1]
@@ -591,6 +738,7 @@ class DenoiserEngine:
             skips = new_skips
             rr = self._from_nchw(mid_res, B * F, hl, wl)
             lib.axpy(x, rr, x, 1.0, x.numel())
+            x.gn_stats = None  # modified in place: the producer's GroupNorm sums no longer describe it
         eps = self.decode(x, skips, temb, kvs, ti, H=hl, W=wl, **kw)
         out = eps.view(B, F, H, W, self.out_channels).permute(0, 1, 4, 2, 3).to(sample.dtype).contiguous()
         return out
@@ -602,6 +750,7 @@ class DenoiserEngine:
             raise ValueError("controlnet_cond is required")
         x_in, temb, kvs, (B, F, H, W) = self._prep_inputs(sample, timestep, ehs, added_time_ids,
                                                           extra_channels=controlnet_cond)
+        self.begin_step()
         kw = dict(B=B, F=F, n_ctx=B, batch_offset=0)
         x, skips, dims, ti = self.encode(x_in, temb, kvs, H=H, W=W, **kw)
         hl, wl = dims[-1]

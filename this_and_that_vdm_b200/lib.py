@@ -28,6 +28,12 @@ class GemmParams(C.Structure):
         ("res1", c_void_p), ("ldr1", c_int), ("s1", c_float),
         ("res2", c_void_p), ("ldr2", c_int), ("s2", c_float),
         ("geglu", c_int), ("out", c_void_p), ("ldo", c_int), ("out_fp32", c_int), ("act", c_int),
+        # normalisation fusions (ABI 3)
+        ("gn_stats_out", c_void_p), ("gn_rows_per_inst", c_int), ("row_sums_out", c_void_p),
+        ("rs_addvec", c_void_p), ("rs_add_rows", c_int), ("rs_add_mod", c_int), ("ld_rs_add", c_int),
+        ("ln_rowsums", c_void_p), ("ln_colsum", c_void_p), ("ln_eps", c_float),
+        ("prevec", c_void_p), ("prevec_rows", c_int), ("prevec_mod", c_int), ("ldpv", c_int),
+        ("ln_row_add", c_void_p),
     ]
 
 
@@ -63,6 +69,7 @@ class GroupNormParams(C.Structure):
         ("rows", c_int), ("rows_per_inst", c_int), ("eps", c_float),
         ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("silu", c_int),
         ("out", c_void_p), ("ldo", c_int),
+        ("pstats1", c_void_p), ("pstats2", c_void_p),
     ]
 
 
@@ -107,8 +114,19 @@ class GestureParams(C.Structure):
     ]
 
 
+class PackLinearParams(C.Structure):
+    _fields_ = [
+        ("w", c_void_p), ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("src_dtype", c_int),
+        ("N", c_int), ("K", c_int), ("geglu", c_int), ("out_row0", c_int), ("ldo", c_int),
+        ("out_w", c_void_p), ("out_bias", c_void_p), ("out_colsum", c_void_p),
+    ]
+
+
 EXPORTS = [
-    "ttvdm_init", "ttvdm_last_error", "ttvdm_abi_version", "ttvdm_launch_count",
+    "ttvdm_init", "ttvdm_destroy", "ttvdm_last_error", "ttvdm_abi_version", "ttvdm_launch_count",
+    "ttvdm_pack_conv_weight", "ttvdm_pack_linear", "ttvdm_pack_vector",
+    "ttvdm_groupnorm_workspace_bytes", "ttvdm_gemm_gn_stats_bytes", "ttvdm_gemm_row_sums_bytes",
+    "ttvdm_gemm_workspace_bytes", "ttvdm_attn_workspace_bytes", "ttvdm_gesture_scratch_bytes",
     "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
     "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
     "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step", "ttvdm_gesture_raster",
@@ -133,6 +151,9 @@ def load() -> C.CDLL:
                 f"{LIB_PATH} is missing: run `python -m this_and_that_vdm_b200.build` (there is no CPU fallback)")
         lib = C.CDLL(str(LIB_PATH))
         lib.ttvdm_launch_count.restype = C.c_uint64
+        for q in ("ttvdm_groupnorm_workspace_bytes", "ttvdm_gemm_gn_stats_bytes", "ttvdm_gemm_row_sums_bytes",
+                  "ttvdm_gemm_workspace_bytes", "ttvdm_attn_workspace_bytes", "ttvdm_gesture_scratch_bytes"):
+            getattr(lib, q).restype = C.c_size_t
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError if a declared symbol is not exported
         _lib = lib
@@ -157,6 +178,12 @@ def init(device: Optional[int] = None) -> None:
 
 def launch_count() -> int:
     return int(load().ttvdm_launch_count())
+
+
+def destroy() -> None:
+    """ttvdm_destroy: forget the process-wide state; the next init() / call initialises again."""
+    _check(load().ttvdm_destroy(), "ttvdm_destroy")
+    _inited_devices.clear()
 
 
 def _stream() -> c_void_p:
@@ -227,7 +254,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0, ldrv: int = 0, s0: float = 1.0,
          res1: Optional[torch.Tensor] = None, ldr1: int = 0, s1: float = 1.0,
          res2: Optional[torch.Tensor] = None, ldr2: int = 0, s2: float = 1.0,
-         geglu: bool = False, ldo: Optional[int] = None, out_fp32: bool = False, act: int = 0) -> None:
+         geglu: bool = False, ldo: Optional[int] = None, out_fp32: bool = False, act: int = 0,
+         gn_stats_out: Optional[torch.Tensor] = None, gn_rows_per_inst: int = 0,
+         row_sums_out: Optional[torch.Tensor] = None, rs_addvec: Optional[torch.Tensor] = None, rs_add_rows: int = 0,
+         rs_add_mod: int = 0,
+         ln_rowsums: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+         prevec: Optional[torch.Tensor] = None, prevec_rows: int = 0, prevec_mod: int = 0, ldpv: int = 0,
+         ln_row_add: Optional[torch.Tensor] = None) -> None:
+    """gn_stats_out: fp64 [M / gn_rows_per_inst, N / 2, 2] (pre-zeroed; the epilogue adds the GroupNorm sums of `out`);
+    row_sums_out: fp32 [N / 32, M, 2] (LayerNorm partial sums of `out`, no zeroing needed); ln_rowsums (= the producer's
+    row_sums_out, [K / 32, M, 2]) / ln_colsum (+ prevec / ln_row_add):
+    LayerNorm of the A operand folded into this GEMM's epilogue — see include/ttvdm.h."""
     p = GemmParams()
     p.mode = mode
     p.a, p.a2, p.k1, p.k2 = _ptr(a), _ptr(a2), k1, k2
@@ -243,6 +280,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     p.ldo = ldo if ldo is not None else (N // 2 if geglu else N)
     p.out_fp32 = int(out_fp32)
     p.act = act
+    p.gn_stats_out, p.gn_rows_per_inst, p.row_sums_out = _ptr(gn_stats_out), gn_rows_per_inst, _ptr(row_sums_out)
+    p.rs_addvec, p.rs_add_rows, p.rs_add_mod, p.ld_rs_add = _ptr(rs_addvec), rs_add_rows, rs_add_mod, N
+    p.ln_rowsums, p.ln_colsum, p.ln_eps = _ptr(ln_rowsums), _ptr(ln_colsum), ln_eps
+    p.prevec, p.prevec_rows, p.prevec_mod, p.ldpv = _ptr(prevec), prevec_rows, prevec_mod, ldpv if ldpv else N
+    p.ln_row_add = _ptr(ln_row_add)
     call("ttvdm_gemm", p)
 
 
@@ -271,13 +313,16 @@ def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) ->
 
 
 def groupnorm(x1, out, stats, gamma, beta, *, c1, rows, rows_per_inst, eps, silu, x2=None, c2=0,
-              ld1=None, ld2=None, ldo=None) -> None:
+              ld1=None, ld2=None, ldo=None, pstats1=None, pstats2=None) -> None:
+    """pstats1 / pstats2: fp64 [n_inst, c / 2, 2] GroupNorm sums written by the epilogue of the GEMM that produced x1 / x2
+    (gemm(gn_stats_out=...)); a source that has them is not read by the statistics pass (stats may then be None)."""
     p = GroupNormParams()
     p.x1, p.c1, p.ld1 = _ptr(x1), c1, c1 if ld1 is None else ld1
     p.x2, p.c2, p.ld2 = _ptr(x2), c2, c2 if ld2 is None else ld2
     p.rows, p.rows_per_inst, p.eps = rows, rows_per_inst, eps
     p.stats, p.gamma, p.beta, p.silu = _ptr(stats), _ptr(gamma), _ptr(beta), int(silu)
     p.out, p.ldo = _ptr(out), (c1 + c2) if ldo is None else ldo
+    p.pstats1, p.pstats2 = _ptr(pstats1), _ptr(pstats2)
     call("ttvdm_groupnorm", p)
 
 
@@ -341,6 +386,42 @@ def sampler_euler_step(latents, eps_u, eps_c, guidance, *, ld_eps, F, h, w, sigm
     p.latents, p.eps_u, p.eps_c, p.ld_eps = _ptr(latents), _ptr(eps_u), _ptr(eps_c), ld_eps
     p.guidance, p.F, p.h, p.w, p.sigma, p.sigma_next = _ptr(guidance), F, h, w, sigma, sigma_next
     call("ttvdm_sampler_euler_step", p)
+
+
+# ---- weight repack entry points (include/ttvdm.h, "Weight repack entry points"): once per model load
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _src(t: torch.Tensor) -> int:
+    if t.dtype not in _DT or not t.is_contiguous():
+        raise TtvdmError(f"pack: source must be a contiguous fp32 / fp16 / bf16 tensor (got {t.dtype})")
+    return _DT[t.dtype]
+
+
+def pack_conv_weight(w: torch.Tensor, out: torch.Tensor, *, cin_pad: int = 0) -> None:
+    """w [cout, cin, *taps] (3x3 -> 9 taps, (3,1,1) -> 3, 1x1 -> 1) -> out bf16 [cout, taps * cin_pad] tap-major."""
+    cout, cin = w.shape[:2]
+    taps = w[0, 0].numel()
+    call_raw("ttvdm_pack_conv_weight", c_void_p(_ptr(w)), _src(w), cout, cin, taps, max(cin_pad, cin), c_void_p(_ptr(out)))
+
+
+def pack_linear(w: torch.Tensor, out_w: torch.Tensor, *, bias=None, gamma=None, beta=None, out_bias=None, out_colsum=None,
+                geglu: bool = False, out_row0: int = 0) -> None:
+    """out_w[row] = bf16(w[n] * gamma); out_colsum[row] = sum_k out_w[row, k]; out_bias[row] = bias[n] + w[n] . beta."""
+    p = PackLinearParams()
+    N = w.shape[0]
+    K = w[0].numel()
+    for t in (bias, gamma, beta):
+        if t is not None and (t.dtype != w.dtype or not t.is_contiguous()):
+            raise TtvdmError("pack_linear: bias / gamma / beta must share the weight's dtype")
+    p.w, p.bias, p.gamma, p.beta, p.src_dtype = _ptr(w), _ptr(bias), _ptr(gamma), _ptr(beta), _src(w)
+    p.N, p.K, p.geglu, p.out_row0, p.ldo = N, K, int(geglu), out_row0, out_w.shape[-1]
+    p.out_w, p.out_bias, p.out_colsum = _ptr(out_w), _ptr(out_bias), _ptr(out_colsum)
+    call("ttvdm_pack_linear", p)
+
+
+def pack_vector(src: torch.Tensor, out: torch.Tensor) -> None:
+    call_raw("ttvdm_pack_vector", c_void_p(_ptr(src)), _src(src), c_size_t(src.numel()), c_void_p(_ptr(out)))
 
 
 # ---- VAE-only entry points (include/ttvdm.h, "VAE either side of the loop")

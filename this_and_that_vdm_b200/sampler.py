@@ -77,6 +77,9 @@ class FusedDenoiser:
         lib.sampler_prepare(latents, self.image_latents, self.cond, self.x_in, c_pad=PAD_IN, B_local=bl,
                             batch_offset=self.batch_offset, F=F, h=h, w=w, sigma=self.sigmas[i])
         kw = dict(B=bl, F=F, n_ctx=self.B, batch_offset=self.batch_offset)
+        self.unet.begin_step()
+        if self.cn is not None:
+            self.cn.begin_step()
         temb_u = self.temb_u[i * bl:(i + 1) * bl]
         x, skips, dims, ti = self.unet.encode(self.x_in, temb_u, self.kv_u, H=h, W=w, **kw)
         hl, wl = dims[-1]
@@ -86,7 +89,7 @@ class FusedDenoiser:
             cx, cskips, _, cti = self.cn.encode(self.x_in, temb_c, self.kv_c, H=h, W=w, **kw)
             cx, _ = self.cn.middle(cx, temb_c, self.kv_c, cti, H=hl, W=wl, **kw)
             # the down path is finished, so the residuals can be accumulated into the skip tensors in place
-            self.cn.zero_convs(cskips, cx, [self.cond_scale] * (len(cskips) + 1), into=skips, mid_into=x)
+            self.cn.zero_convs(cskips, cx, [self.cond_scale] * (len(cskips) + 1), into=skips, mid_into=x, n_img=bl * F)
         return self.unet.decode(x, skips, temb_u, self.kv_u, ti, H=hl, W=wl, **kw)
 
     def euler_update(self, i: int, latents: torch.Tensor, eps_u: torch.Tensor, eps_c: torch.Tensor) -> None:

@@ -234,7 +234,157 @@ def case_sampler(F=14, h=8, w=12, seed=0):
     return max(e1, rel_l2(lat2, refl))
 
 
+# ------------------------------------------------------------------------------------------------ norm fusions (ABI 3)
+def _gn_ref(x, n_inst, rpi, C, gamma, beta, eps, silu):
+    xr = x.float().reshape(n_inst, rpi, C).permute(0, 2, 1)
+    ref = Fn.group_norm(xr, 32, gamma, beta, eps)
+    if silu:
+        ref = Fn.silu(ref)
+    return ref.permute(0, 2, 1).reshape(n_inst * rpi, C)
+
+
+def case_gemm_gn_stats(mode="linear", M=0, N=320, K=320, rpi=0, n=2, H=24, W=40, Cin=64, B=2, F=5, S=200, res=True,
+                       concat=False, seed=0):
+    """A GEMM whose epilogue accumulates the GroupNorm pair sums of its output, followed by ttvdm_groupnorm that uses
+    them (no statistics pass): compared with torch group_norm of the GEMM's own bf16 output. Also returns the error of
+    the pair sums themselves against fp64 sums of the stored tensor (max of the two)."""
+    if mode == "linear":
+        a = bf(g(M, K, seed=seed)); w = bf(g(N, K, seed=seed + 1, scale=K ** -0.5)); b = g(N, seed=seed + 2)
+        r1 = bf(g(M, N, seed=seed + 3)) if res else None
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        st = torch.zeros((M // rpi) * N, dtype=torch.float64, device=DEV)
+        lib.gemm(a, w, out, M=M, N=N, k1=K, bias=b, res1=r1, gn_stats_out=st, gn_rows_per_inst=rpi)
+    elif mode == "conv":
+        M, rpi_ = n * H * W, (rpi or H * W)
+        rpi = rpi_
+        x = bf(g(n, H, W, Cin, seed=seed)); wk = bf(g(N, 9 * Cin, seed=seed + 1, scale=(9 * Cin) ** -0.5)); b = g(N, seed=seed + 2)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        st = torch.zeros((M // rpi) * N, dtype=torch.float64, device=DEV)
+        lib.gemm(x, wk, out, M=M, N=N, k1=Cin, mode=lib.A_CONV3X3, n_img=n, H=H, W=W, bias=b, gn_stats_out=st,
+                 gn_rows_per_inst=rpi)
+    else:
+        M = B * F * S
+        rpi = rpi or F * S
+        x = bf(g(B, F, S, N, seed=seed)); wk = bf(g(N, 3 * N, seed=seed + 1, scale=(3 * N) ** -0.5)); b = g(N, seed=seed + 2)
+        r1 = bf(g(M, N, seed=seed + 3))
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        st = torch.zeros((M // rpi) * N, dtype=torch.float64, device=DEV)
+        lib.gemm(x, wk, out, M=M, N=N, k1=N, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=b, res1=r1, gn_stats_out=st,
+                 gn_rows_per_inst=rpi)
+    n_inst = M // rpi
+    v = out.double().view(n_inst, rpi, N // 2, 2)
+    ref_st = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).reshape(-1)
+    e_st = float((st - ref_st).abs().max() / ref_st.abs().max())
+    # consumer: GroupNorm (+ optional second source WITHOUT producer statistics: mixed mode)
+    c2 = 64 if concat else 0
+    x2 = bf(g(M, c2, seed=seed + 7)) if concat else None
+    C = N + c2
+    gamma = g(C, seed=seed + 4) * 0.1 + 1
+    beta = g(C, seed=seed + 5) * 0.1
+    y = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    ws = torch.empty(n_inst * 64, dtype=torch.float64, device=DEV) if concat else None
+    n0 = lib.launch_count()
+    lib.groupnorm(out, y, ws, gamma, beta, c1=N, rows=M, rows_per_inst=rpi, eps=1e-6, silu=True, x2=x2, c2=c2, pstats1=st)
+    launches = lib.launch_count() - n0
+    assert launches == (2 if concat else 1), f"groupnorm launched {launches} kernels"
+    xin = torch.cat([out, x2], 1) if concat else out
+    ref = _gn_ref(xin, n_inst, rpi, C, gamma, beta, 1e-6, True)
+    torch.cuda.synchronize()
+    return max(rel_l2(y, ref), e_st * 100)  # e_st must be < 1e-4 * ... (fp32 partials): scaled so TOL applies
+
+
+def case_gemm_ln_fold(M=1000, C=320, N=960, geglu=False, posemb=False, F=7, S=0, direct_producer=False, seed=0):
+    """Producer GEMM writes h (+ row sums, optionally over h + positional embedding); consumer GEMM applies the folded
+    LayerNorm in its epilogue. Reference: torch layer_norm of the producer's bf16 output, then the linear (+ GEGLU)."""
+    Kp = 4 * C if direct_producer else C
+    a = bf(g(M, Kp, seed=seed)); wp = bf(g(C, Kp, seed=seed + 1, scale=Kp ** -0.5)); bp = g(C, seed=seed + 2)
+    r1 = bf(g(M, C, seed=seed + 3) * 2)
+    h = torch.empty(M, C, dtype=torch.bfloat16, device=DEV)
+    rs = torch.empty(C // 32, M, 2, dtype=torch.float32, device=DEV)
+    pos = g(F, C, seed=seed + 9) * 0.5 if posemb else None
+    S = S or (M // F if posemb else 0)
+    lib.gemm(a, wp, h, M=M, N=C, k1=Kp, bias=bp, res1=r1, row_sums_out=rs, rs_addvec=pos, rs_add_rows=S, rs_add_mod=F)
+    gamma = g(C, seed=seed + 4) * 0.2 + 1
+    beta = g(C, seed=seed + 5) * 0.2
+    w = g(N, C, seed=seed + 6, scale=C ** -0.5)
+    b = g(N, seed=seed + 7)
+    wf = bf(w * gamma[None, :])
+    bias_f = (b + w @ beta).contiguous()
+    cs = wf.float().sum(1).contiguous()
+    out = torch.empty(M, N // 2 if geglu else N, dtype=torch.bfloat16, device=DEV)
+    kw = {}
+    if posemb:
+        pv = (bf(pos).float() @ wf.float().t()).contiguous()
+        kw = dict(prevec=pv, prevec_rows=S, prevec_mod=F)
+    lib.gemm(h, wf, out, M=M, N=N, k1=C, bias=bias_f, geglu=geglu, ln_rowsums=rs, ln_colsum=cs, ln_eps=1e-5, **kw)
+    x = h.float()
+    if posemb:
+        x = x + pos[(torch.arange(M, device=DEV) // S) % F]
+    ref = Fn.layer_norm(x, (C,), gamma, beta, 1e-5) @ w.t() + b
+    if geglu:
+        ref = ref[:, 0::2] * Fn.gelu(ref[:, 1::2])
+    torch.cuda.synchronize()
+    return rel_l2(out, ref)
+
+
+def case_pack(dtype=torch.float32, seed=0):
+    """Repack entry points against plain torch: conv tap-major layout with channel padding, LayerNorm-folded GEGLU
+    interleave (+ folded bias, column sums), fused row offsets, fp32 vector cast. Returns the worst relative error."""
+    errs = []
+    w = g(40, 24, 3, 3, seed=seed).to(dtype)
+    out = torch.empty(40, 9 * 64, dtype=torch.bfloat16, device=DEV)
+    lib.pack_conv_weight(w, out, cin_pad=64)
+    ref = torch.zeros(40, 3, 3, 64, device=DEV)
+    ref[..., :24] = w.float().permute(0, 2, 3, 1)
+    errs.append(rel_l2(out, bf(ref.reshape(40, -1))))
+    tw = g(48, 48, 3, 1, 1, seed=seed + 1).to(dtype)
+    out = torch.empty(48, 3 * 48, dtype=torch.bfloat16, device=DEV)
+    lib.pack_conv_weight(tw, out)
+    errs.append(rel_l2(out, bf(tw.float().reshape(48, 48, 3).permute(0, 2, 1).reshape(48, -1))))
+    N, K = 96, 320
+    lw, lb = g(N, K, seed=seed + 2, scale=K ** -0.5).to(dtype), g(N, seed=seed + 3).to(dtype)
+    gamma, beta = (g(K, seed=seed + 4) * 0.2 + 1).to(dtype), (g(K, seed=seed + 5) * 0.2).to(dtype)
+    ow = torch.zeros(N + 10, K, dtype=torch.bfloat16, device=DEV)
+    ob = torch.zeros(N + 10, dtype=torch.float32, device=DEV)
+    oc = torch.zeros(N + 10, dtype=torch.float32, device=DEV)
+    lib.pack_linear(lw, ow, bias=lb, gamma=gamma, beta=beta, out_bias=ob, out_colsum=oc, geglu=True, out_row0=10)
+    order = torch.stack([torch.arange(N // 2), torch.arange(N // 2) + N // 2], 1).reshape(-1).to(DEV)
+    wf = bf(lw.float() * gamma.float()[None, :])[order]
+    errs.append(rel_l2(ow[10:], wf))
+    errs.append(rel_l2(ob[10:], (lb.float() + lw.float() @ beta.float())[order]))
+    errs.append(rel_l2(oc[10:], wf.float().sum(1)))
+    errs.append(float(ow[:10].float().abs().max()))  # rows before out_row0 untouched
+    v = g(777, seed=seed + 6).to(dtype)
+    o = torch.empty(777, dtype=torch.float32, device=DEV)
+    lib.pack_vector(v, o)
+    errs.append(rel_l2(o, v.float()))
+    torch.cuda.synchronize()
+    return max(errs)
+
+
 CASES = [
+    ("pack_fp32", lambda: case_pack(torch.float32)),
+    ("pack_fp16", lambda: case_pack(torch.float16)),
+    ("pack_bf16", lambda: case_pack(torch.bfloat16)),
+    ("gemm_gnstats_linear_tma", lambda: case_gemm_gn_stats("linear", M=28 * 150, N=320, K=320, rpi=150)),
+    ("gemm_gnstats_linear_straddle", lambda: case_gemm_gn_stats("linear", M=20 * 24, N=1280, K=1280, rpi=24)),
+    ("gemm_gnstats_linear_direct", lambda: case_gemm_gn_stats("linear", M=7 * 144, N=320, K=2880, rpi=144)),
+    ("gemm_gnstats_linear_mixed_concat", lambda: case_gemm_gn_stats("linear", M=6 * 100, N=64, K=64, rpi=100, concat=True)),
+    ("gemm_gnstats_conv_direct", lambda: case_gemm_gn_stats("conv", n=3, H=18, W=32, Cin=320, N=320)),
+    ("gemm_gnstats_conv_tma_5d", lambda: case_gemm_gn_stats("conv", n=4, H=9, W=16, Cin=64, N=128, rpi=2 * 9 * 16)),
+    ("gemm_gnstats_conv_ragged", lambda: case_gemm_gn_stats("conv", n=2, H=7, W=13, Cin=64, N=64)),
+    ("gemm_gnstats_tconv_5d", lambda: case_gemm_gn_stats("tconv", B=2, F=5, S=200, N=320)),
+    ("gemm_gnstats_tconv_4d", lambda: case_gemm_gn_stats("tconv", B=2, F=4, S=96, N=640, rpi=96)),
+    ("gemm_gnstats_tconv_direct", lambda: case_gemm_gn_stats("tconv", B=1, F=3, S=150, N=1280)),
+    ("gemm_lnfold_qkv", lambda: case_gemm_ln_fold()),
+    ("gemm_lnfold_q_640", lambda: case_gemm_ln_fold(M=777, C=640, N=640)),
+    ("gemm_lnfold_geglu", lambda: case_gemm_ln_fold(M=515, C=320, N=2560, geglu=True)),
+    ("gemm_lnfold_geglu_posemb", lambda: case_gemm_ln_fold(M=7 * 90, C=320, N=2560, geglu=True, posemb=True)),
+    ("gemm_lnfold_direct_producer_posemb", lambda: case_gemm_ln_fold(M=7 * 64, C=320, N=2560, geglu=True, posemb=True,
+                                                                     direct_producer=True)),
+    ("gemm_lnfold_1280", lambda: case_gemm_ln_fold(M=300, C=1280, N=3840)),
+    ("gemm_lnfold_c64", lambda: case_gemm_ln_fold(M=200, C=64, N=192)),
+] + [
     ("gemm_linear_320", lambda: case_gemm_linear()),
     ("gemm_linear_bigN_res", lambda: case_gemm_linear(M=777, N=1280, K=640, res=True)),
     ("gemm_linear_geglu", lambda: case_gemm_linear(M=515, N=2560, K=320, geglu=True)),
