@@ -145,16 +145,23 @@ def run_ours(args):
     guidance = torch.linspace(1.0, 3.0, FRAMES)
     from this_and_that_vdm_b200.sharding import broadcast_conditioning, gather_latents
 
-    # one video per rank (weak scaling); rank 0 owns the conditioning of all videos of a round
-    cond_all = synth_inputs(h, w, world, seed=0) if rank == 0 else None
+    # K videos per round (default: one per rank = weak scaling); rank 0 owns the conditioning of all of them. The batch is
+    # partitioned by sharding.plan(): whole CFG pairs per rank when K >= N (no per-step communication), split pairs
+    # (uncond / cond halves on two ranks, one 2-rank exchange of the noise prediction per step) when K < N.
+    from this_and_that_vdm_b200.sharding import plan, run_sharded
+    K = args.videos if args.videos > 0 else world
+    cond_all = synth_inputs(h, w, K, seed=0) if rank == 0 else None
     den = FusedDenoiser(unet._get_engine(), cn._get_engine())
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    my_plan = plan(K, world)[rank]
+    split_pairs = sum(1 for a in plan(K, world)[0] if a.b_local == 1) > 0 or any(
+        a.b_local == 1 for r in plan(K, world) for a in r)
 
-    def one_video_resident(c) -> torch.Tensor:
-        idx = [rank, world + rank]
-        state = c["latents"][rank].clone().contiguous()
+    def one_video_resident(c, v) -> torch.Tensor:
+        idx = [v, K + v]
+        state = c["latents"][v].clone().contiguous()
         den.prepare(c["encoder_hidden_states"][idx], c["image_latents"][idx], c["added_time_ids"][idx], sigmas,
-                    timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][rank])
+                    timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][v])
         for i in range(NUM_STEPS):
             den.step(i, state)
         return state
@@ -166,12 +173,10 @@ def run_ours(args):
 
     def round_resident():
         if world > 1:
-            c = broadcast_conditioning(cond_dev if rank == 0 else None, dev)
-        else:
-            c = cond_dev
-        st = one_video_resident(c)
-        if world > 1:
-            gather_latents(st[None].contiguous())
+            return run_sharded(K, cond_dev if rank == 0 else None, dev, lambda: den, sigmas, timesteps, guidance)
+        st = None
+        for v in range(K):
+            st = one_video_resident(cond_dev, v)
         return st
 
     cond_dev = {k: v.to(dev) for k, v in cond_all.items()} if rank == 0 else None
@@ -179,7 +184,7 @@ def run_ours(args):
         # ncu helper: `ncu --profile-from-start off ... python bench.py --profile-only` captures exactly ONE Euler step
         c = cond_dev
         state = c["latents"][0].clone().contiguous()
-        den.prepare(c["encoder_hidden_states"][[0, world]], c["image_latents"][[0, world]], c["added_time_ids"][[0, world]],
+        den.prepare(c["encoder_hidden_states"][[0, K]], c["image_latents"][[0, K]], c["added_time_ids"][[0, K]],
                     sigmas, timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][0])
         den.step(0, state)
         torch.cuda.synchronize()
@@ -211,40 +216,60 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per_video = ms / args.steps
-    value = world * FRAMES / (ms_per_video / 1e3)
+    ms_per_video = ms / args.steps          # one "step" of this bench = one round of K videos
+    value = K * FRAMES / (ms_per_video / 1e3)
 
-    # ---------------- e2e through the public pipeline API with pinned host buffers
-    pipe = StableVideoDiffusionControlNetPipeline.from_pretrained(None, unet=unet).to(dev)
-    host = synth_inputs(h, w, 1, seed=rank)
-    host = {k: v.pin_memory() for k, v in host.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    out_host = torch.empty(1, FRAMES, 4, h, w, dtype=torch.float32).pin_memory()
-
-    def one_video_e2e():
-        res = pipe(controlnet=cn, height=args.height, width=args.width, num_frames=FRAMES,
-                   num_inference_steps=NUM_STEPS, min_guidance_scale=1.0, max_guidance_scale=3.0, fps=7,
-                   motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent", guess_mode=False,
-                   latents=host["latents"].to(dev, non_blocking=True) / sched.init_noise_sigma,
-                   encoder_hidden_states=host["encoder_hidden_states"].to(dev, non_blocking=True),
-                   image_latents=host["image_latents"].to(dev, non_blocking=True),
-                   controlnet_cond_latents=host["controlnet_cond"][0].to(dev, non_blocking=True))
-        out_host.copy_(res.frames, non_blocking=True)
-        torch.cuda.synchronize()
-
-    one_video_e2e()  # warm
-    sync()
+    # ---------------- e2e through the public API with pinned HOST buffers (H2D of the inputs and D2H of the result inside
+    # the timed region). N = 1: StableVideoDiffusionControlNetPipeline.__call__ (latent mode), K videos one after the
+    # other. N > 1: sharding.run_sharded — rank 0 uploads the pinned conditioning pack, ONE broadcast, every rank
+    # denoises its share, ONE gather, rank 0 reads the latents back.
     n_e2e = max(5, min(args.steps, 8)) if not args.quick_e2e else 1
+    if world == 1:
+        pipe = StableVideoDiffusionControlNetPipeline.from_pretrained(None, unet=unet).to(dev)
+        host = synth_inputs(h, w, 1, seed=rank)
+        host = {k: v.pin_memory() for k, v in host.items()}
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) * K
+        out_host = torch.empty(1, FRAMES, 4, h, w, dtype=torch.float32).pin_memory()
+        d2h = out_host.numel() * 4 * K
+        e2e_api = "StableVideoDiffusionControlNetPipeline.__call__ (latent mode)"
+
+        def one_round_e2e():
+            for _ in range(K):
+                res = pipe(controlnet=cn, height=args.height, width=args.width, num_frames=FRAMES,
+                           num_inference_steps=NUM_STEPS, min_guidance_scale=1.0, max_guidance_scale=3.0, fps=7,
+                           motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent", guess_mode=False,
+                           latents=host["latents"].to(dev, non_blocking=True) / sched.init_noise_sigma,
+                           encoder_hidden_states=host["encoder_hidden_states"].to(dev, non_blocking=True),
+                           image_latents=host["image_latents"].to(dev, non_blocking=True),
+                           controlnet_cond_latents=host["controlnet_cond"][0].to(dev, non_blocking=True))
+                out_host.copy_(res.frames, non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        host = {k: v.pin_memory() for k, v in cond_all.items()} if rank == 0 else None
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) if rank == 0 else 0
+        out_host = torch.empty(K, FRAMES, 4, h, w, dtype=torch.float32).pin_memory() if rank == 0 else None
+        d2h = out_host.numel() * 4 if rank == 0 else 0
+        e2e_api = "this_and_that_vdm_b200.sharding.run_sharded (pinned host conditioning -> latents on the host)"
+
+        def one_round_e2e():
+            c = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if rank == 0 else None
+            final = run_sharded(K, c, dev, lambda: den, sigmas, timesteps, guidance)
+            if rank == 0:
+                out_host.copy_(final, non_blocking=True)
+            torch.cuda.synchronize()
+
+    one_round_e2e()  # warm
+    sync()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        one_video_e2e()
+        one_round_e2e()
     sync()
     e2e_s = (time.perf_counter() - t0) / n_e2e
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * FRAMES / e2e_s
+    e2e_value = K * FRAMES / e2e_s
 
     # ---------------- roofline pass: CUDA events around every C-ABI call of ONE Euler step (rank 0)
     roof = None
@@ -252,7 +277,7 @@ def run_ours(args):
     if rank == 0:
         peaks = load_peaks()
         c = cond_dev
-        idx = [0, world]
+        idx = [0, K]
         state = c["latents"][0].clone().contiguous()
         den.prepare(c["encoder_hidden_states"][idx], c["image_latents"][idx], c["added_time_ids"][idx], sigmas,
                     timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][0])
@@ -318,15 +343,19 @@ def run_ours(args):
             "metric": "frames/sec for 14-frame 576x1024 VGL, 25 Euler steps" if (args.height, args.width) == (576, 1024)
             else f"frames/sec for 14-frame {args.height}x{args.width} VGL, 25 Euler steps",
             "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_video, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_per_video, 2), "higher_is_better": True,
+            "scaling": "weak" if args.videos <= 0 else "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, seeded N(0,1) latents/conditioning)",
             "config": {"workload": f"VGL (UNet+GestureNet) 25-step Euler, 14x{args.height}x{args.width}, CFG pair (B=2) per video, "
-                                   f"one video per GPU", "step": "one video = 25 Euler steps", "latent": [FRAMES, 4, h, w],
-                       "parallelism": f"dp{world} (whole CFG pairs per rank; 1 conditioning broadcast + 1 latent gather per round)",
+                                   f"{K} video(s) per round on {world} GPU(s)", "videos": K,
+                       "step": f"one round = {K} video(s) x 25 Euler steps", "latent": [FRAMES, 4, h, w],
+                       "parallelism": f"dp{world}: " + ("split CFG pairs (uncond / cond halves on two ranks, one 2-rank exchange of "
+                                                        "the noise prediction per Euler step)" if split_pairs else
+                                                        "whole CFG pairs per rank, no per-step communication") +
+                                      "; 1 conditioning broadcast + 1 latent gather per round",
                        "l2": "192 MB flush write between videos; per-step working set >> 126 MB L2"},
             "e2e": {"value": round(e2e_value, 4), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(out_host.numel() * 4), "api": "StableVideoDiffusionControlNetPipeline.__call__ (latent mode)",
-                    "videos_timed": n_e2e},
+                    "d2h_bytes_per_step": int(d2h), "api": e2e_api, "rounds_timed": n_e2e, "videos_timed": n_e2e * K},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernel_shares": shares,
             "gemm_shapes": gemm_shapes if rank == 0 else None,
             "cpu_baseline": cpu,
@@ -336,7 +365,7 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
         try:
             (ROOT / "gpurun_out").mkdir(exist_ok=True)
-            (ROOT / "gpurun_out" / f"bench_last_{args.height}x{args.width}_n{world}.json").write_text(json.dumps(line, indent=1))
+            (ROOT / "gpurun_out" / f"bench_last_{args.height}x{args.width}_n{world}_k{K}.json").write_text(json.dumps(line, indent=1))
         except Exception:  # noqa: BLE001
             pass
     if world > 1:
@@ -506,6 +535,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--videos", type=int, default=0,
+                    help="videos per round (BASELINE.json configs[4]); default = one per GPU (weak scaling)")
     ap.add_argument("--height", type=int, default=576)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -272,7 +272,7 @@ class SVDPipelineBase:
         do_cfg = encoder_hidden_states.shape[0] == 2 * N
         h, w = latents.shape[-2:]
         cn_engine = controlnet._get_engine() if controlnet is not None else None
-        den = FusedDenoiser(self.unet._get_engine(), cn_engine)
+        den = FusedDenoiser.cached(self.unet._get_engine(), cn_engine)
         out_dtype = latents.dtype
         result = []
         for n in range(N):

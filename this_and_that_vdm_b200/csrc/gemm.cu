@@ -181,15 +181,16 @@ __device__ __forceinline__ int tile_instance(const GemmArgs& g, const TileCoord&
 }
 
 // Epilogue warps only (kEpiWarps * 32 threads, named barrier 1): add the CTA's shared-memory GroupNorm accumulators
-// ([N / 2][2] floats: per channel pair sum / sum of squares over the tiles seen since the last flush) to the global fp64
-// bins of instance `inst`, and clear them.
+// (4 copies, one per TMEM lane quarter, of [N / 2][2] floats: per channel pair sum / sum of squares over the tiles seen
+// since the last flush; a copy is only ever touched by the warps of its quarter, each on its own columns, so plain
+// read-modify-write is race free — shared-memory float atomics are CAS loops) to the global fp64 bins of `inst`.
 __device__ __forceinline__ void gn_flush(const GemmArgs& g, float* acc, int inst, int epi_tid) {
   named_bar_sync(1, kEpiWarps * 32);
   if (inst >= 0) {
     for (int i = epi_tid; i < g.N; i += kEpiWarps * 32) {
-      const float v = acc[i];
+      const float v = (acc[i] + acc[g.N + i]) + (acc[2 * g.N + i] + acc[3 * g.N + i]);  // the four lane-quarter copies
       if (v != 0.f) red_add_f64(g.gn_stats + (long long)inst * g.N + i, (double)v);
-      acc[i] = 0.f;
+      acc[i] = acc[g.N + i] = acc[2 * g.N + i] = acc[3 * g.N + i] = 0.f;
     }
   }
   named_bar_sync(1, kEpiWarps * 32);
@@ -229,9 +230,14 @@ __device__ __forceinline__ void gn_stats_chunk(const GemmArgs& g, const float (&
 #pragma unroll
     for (int i = 0; i < 32; ++i) q[i] = valid ? a[i] : 0.f;
     const float cs = warp_colsum32(q, lane);
-    if (col < g.N) {  // lane c holds column col0 + c; bins are per channel PAIR: (sum, sum of squares)
-      atomicAdd(acc + (col >> 1) * 2, cs);
-      atomicAdd(acc + (col >> 1) * 2 + 1, cq);
+    // lane c holds column col0 + c; bins are per channel PAIR (sum, sum of squares): fold the odd column into the even lane
+    const float cs2 = cs + __shfl_down_sync(0xffffffffu, cs, 1), cq2 = cq + __shfl_down_sync(0xffffffffu, cq, 1);
+    if ((lane & 1) == 0 && col < g.N) {
+      float2* d = reinterpret_cast<float2*>(acc + col);  // this quarter's copy; no other warp touches these columns now
+      float2 o = *d;
+      o.x += cs2;
+      o.y += cq2;
+      *d = o;
     }
     return;
   }
@@ -262,11 +268,13 @@ __device__ __forceinline__ void gn_stats_chunk(const GemmArgs& g, const float (&
 
 // Direct epilogue of one 32-column chunk (one row per lane). Every lane of the warp calls it (rows that do not exist
 // with valid = false): the GroupNorm statistics are a warp-wide reduction.
+template <int kFeat>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&v)[32], long long out_row, int col0,
                                                const float* rv, bool valid, int lane, float* gn_acc) {
+  constexpr bool kRs = kFeat == 2, kGn = kFeat == 3;
   float a[32];
   const bool full = (col0 + 32 <= g.N) && ((g.N & 7) == 0);
-  const bool stats = (g.gn_stats != nullptr || g.row_sums != nullptr) && full && !g.out_fp32 && !g.geglu;
+  const bool stats = (kRs || kGn) && full;  // host: statistics need bf16, non-GEGLU output with N % 32 == 0
   if (valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
@@ -383,26 +391,34 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
             *(reinterpret_cast<uint4*>(o) + i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           if (stats) {
             // statistics of exactly what the consumer will read: the bf16-rounded values
-            float rs = 0.f, rq = 0.f;
-            const float* av = (g.row_sums != nullptr && g.rs_addvec != nullptr)
-                                  ? g.rs_addvec + (long long)((out_row / g.rs_add_rows) % g.rs_add_mod) * g.ld_rs_add + col0
-                                  : nullptr;
+            if (kRs) {
+              uint64_t rs2 = 0ull, rq2 = 0ull;
+              const float* av = g.rs_addvec != nullptr
+                                    ? g.rs_addvec + (long long)((out_row / g.rs_add_rows) % g.rs_add_mod) * g.ld_rs_add + col0
+                                    : nullptr;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 f = unpack_bf16(pk[i]);
-              a[2 * i] = f.x;
-              a[2 * i + 1] = f.y;
-              float2 e = f;
-              if (av != nullptr) {
-                const float2 d = __ldg(reinterpret_cast<const float2*>(av) + i);
-                e.x += d.x;
-                e.y += d.y;
+              for (int i = 0; i < 16; ++i) {
+                uint64_t f2 = pack_f32x2(a[2 * i], a[2 * i + 1]);
+                if (av != nullptr) {
+                  const float2 d = __ldg(reinterpret_cast<const float2*>(av) + i);
+                  f2 = add_f32x2(f2, pack_f32x2(d.x, d.y));
+                }
+                rs2 = add_f32x2(rs2, f2);
+                rq2 = fma_f32x2(f2, f2, rq2);
               }
-              rs += e.x + e.y;
-              rq = fmaf(e.x, e.x, fmaf(e.y, e.y, rq));
+              float sa, sb, qa, qb;
+              unpack_f32x2(rs2, sa, sb);
+              unpack_f32x2(rq2, qa, qb);
+              *reinterpret_cast<float2*>(g.row_sums + ((long long)(col0 >> 5) * g.M + out_row) * 2) = make_float2(sa + sb, qa + qb);
             }
-            if (g.row_sums != nullptr)
-              *reinterpret_cast<float2*>(g.row_sums + ((long long)(col0 >> 5) * g.M + out_row) * 2) = make_float2(rs, rq);
+            if (kGn) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {  // GroupNorm sums are taken over the stored (rounded) values
+                const float2 f = unpack_bf16(pk[i]);
+                a[2 * i] = f.x;
+                a[2 * i + 1] = f.y;
+              }
+            }
           }
         } else {
           for (int i = 0; i < 32; ++i)
@@ -411,14 +427,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       }
     }
   }
-  if (stats && g.gn_stats != nullptr) gn_stats_chunk(g, a, valid, out_row, col0, lane, gn_acc);  // whole warp
+  if (kGn && stats) gn_stats_chunk(g, a, valid, out_row, col0, lane, gn_acc);  // whole warp
 }
 
-template <int kCtas>
+// kFeat selects ONE normalisation fusion so that every variant only carries its own epilogue code and registers:
+//   0 plain   1 LayerNorm of A folded in (consumer)   2 LayerNorm row sums of the output (producer)
+//   3 GroupNorm pair sums of the output (producer)
+template <int kCtas, int kFeat>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
             const __grid_constant__ CUtensorMap tmRes, const GemmArgs g) {
+  constexpr bool kLn = kFeat == 1, kRs = kFeat == 2, kGn = kFeat == 3;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -438,8 +458,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* bres = tiles + g.stages * stage_bytes + (g.tma_epi ? kEpiWarps * kEpiBufBytes : 0);
   // GroupNorm accumulators of this CTA ([N / 2][2] floats), behind everything else
   float* gn_acc_base = reinterpret_cast<float*>(bres + (g.b_resident ? g.taps * g.kc_per_tap * b_chunk_bytes : 0));
-  if (g.gn_stats != nullptr)
-    for (int i = threadIdx.x; i < g.N; i += kNumThreads) gn_acc_base[i] = 0.f;
+  if (kGn)
+    for (int i = threadIdx.x; i < 4 * g.N; i += kNumThreads) gn_acc_base[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -601,14 +621,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int col0 = t.n0 + strip;
         const bool active = (strip < g.block_n) && (col0 < g.N);
         float* gn_acc = nullptr;
-        if (g.gn_stats != nullptr) {
+        if (kGn) {
           const int ti = tile_instance(g, t);
           if (ti >= 0) {
             if (ti != cur_inst) {
               if (cur_inst >= 0) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
               cur_inst = ti;
             }
-            gn_acc = gn_acc_base;
+            gn_acc = gn_acc_base + q * g.N;  // this lane quarter's copy
           }
         }
         // box coordinates of the warp's 32 tile rows
@@ -654,14 +674,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         const float* rv = nullptr;
         if (g.rowvec != nullptr && my_valid) rv = g.rowvec + (my_row / g.rows_per_vec) * g.ldrv;
-        float ln_mean = 0.f, ln_rstd = 1.f;
+        float ln_nrm = 0.f, ln_rstd = 1.f;  // ln_nrm = -rstd * mean
         const float* pv = nullptr;
-        if (g.ln_rowsums != nullptr && my_valid) {
+        if (kLn && my_valid) {
           float2 rs = make_float2(0.f, 0.f);
-          for (int j = 0; j < g.ln_parts; ++j) {  // [K / 32][M][2]: coalesced across the warp's 32 rows
-            const float2 pj = __ldg(reinterpret_cast<const float2*>(g.ln_rowsums) + (long long)j * g.M + my_row);
-            rs.x += pj.x;
-            rs.y += pj.y;
+          // [K / 32][M][2], coalesced across the warp's 32 rows; 10 loads in flight at a time (a one-at-a-time loop is a
+          // chain of L2 latencies at the head of every tile's epilogue: measured +80 % on the level-0 qkv GEMM)
+          for (int j0 = 0; j0 < g.ln_parts; j0 += 10) {
+            float2 pj[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u)
+              pj[u] = (j0 + u < g.ln_parts)
+                          ? __ldg(reinterpret_cast<const float2*>(g.ln_rowsums) + (long long)(j0 + u) * g.M + my_row)
+                          : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 10; ++u) {
+              rs.x += pj[u].x;
+              rs.y += pj[u].y;
+            }
           }
           if (g.prevec_mod > 0) {
             const int pi = (int)((my_row / g.prevec_rows) % g.prevec_mod);
@@ -672,11 +702,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               rs.y += ra.y;
             }
           }
-          ln_mean = rs.x * g.ln_inv_k;
+          const float ln_mean = rs.x * g.ln_inv_k;
           ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, rs.y * g.ln_inv_k), 0.f) + g.ln_eps);
+          ln_nrm = -ln_rstd * ln_mean;
         }
-        float row_s = 0.f, row_q = 0.f;  // LayerNorm sums of this lane's row over the warp's strip
-        const float* rs_av = (g.row_sums != nullptr && g.rs_addvec != nullptr && my_valid)
+        uint64_t row_s2 = 0ull, row_q2 = 0ull;  // LayerNorm sums of this lane's row over one chunk (two f32x2 lanes each)
+        const float* rs_av = (kRs && g.rs_addvec != nullptr && my_valid)
                                  ? g.rs_addvec + (long long)((my_row / g.rs_add_rows) % g.rs_add_mod) * g.ld_rs_add
                                  : nullptr;
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -697,8 +728,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             float a[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(v[i]);
-            if (g.ln_rowsums != nullptr && gc + 32 <= g.N) {
-              // LayerNorm of the A operand folded in: rstd * (acc + prevec - mean * colsum) (bias is added below)
+            if (kLn && gc + 32 <= g.N) {
+              // LayerNorm of the A operand folded in:  rstd * (acc + prevec) + (bias - rstd * mean * colsum)
               if (pv != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -709,12 +740,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.ln_colsum + gc + i));
-                a[i] = ln_rstd * fmaf(-ln_mean, c4.x, a[i]);
-                a[i + 1] = ln_rstd * fmaf(-ln_mean, c4.y, a[i + 1]);
-                a[i + 2] = ln_rstd * fmaf(-ln_mean, c4.z, a[i + 2]);
-                a[i + 3] = ln_rstd * fmaf(-ln_mean, c4.w, a[i + 3]);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + gc + i));
+                a[i] = fmaf(a[i], ln_rstd, fmaf(c4.x, ln_nrm, b4.x));
+                a[i + 1] = fmaf(a[i + 1], ln_rstd, fmaf(c4.y, ln_nrm, b4.y));
+                a[i + 2] = fmaf(a[i + 2], ln_rstd, fmaf(c4.z, ln_nrm, b4.z));
+                a[i + 3] = fmaf(a[i + 3], ln_rstd, fmaf(c4.w, ln_nrm, b4.w));
               }
-            }
+            } else
             if (gc + 32 <= g.N) {
               if (g.bias != nullptr) {
 #pragma unroll
@@ -790,26 +822,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
               const uint4 pk4 = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
               *sp = pk4;
-              if (g.row_sums != nullptr) {
-                const uint32_t w4[4] = {pk4.x, pk4.y, pk4.z, pk4.w};
+              if (kRs) {
+                // LayerNorm sums from the fp32 values (the bf16 rounding of the stored copy averages out over a row);
+                // packed f32x2 adds / FMAs: the level-0 epilogues are issue bound, every instruction counts
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float2 f = unpack_bf16(w4[k]);  // the rounded values the consumer will read
+                  uint64_t f2 = pack_f32x2(o[2 * k], o[2 * k + 1]);
                   if (rs_av != nullptr) {
                     const float2 d = __ldg(reinterpret_cast<const float2*>(rs_av + gc + pc * 8) + k);
-                    f.x += d.x;
-                    f.y += d.y;
+                    f2 = add_f32x2(f2, pack_f32x2(d.x, d.y));
                   }
-                  row_s += f.x + f.y;
-                  row_q = fmaf(f.x, f.x, fmaf(f.y, f.y, row_q));
+                  row_s2 = add_f32x2(row_s2, f2);
+                  row_q2 = fma_f32x2(f2, f2, row_q2);
                 }
               }
             }
-            if (g.row_sums != nullptr && my_valid && gc + 32 <= g.N) {
+            if (kRs && my_valid && gc + 32 <= g.N) {
               // one (32-column chunk, row) slot per lane: 32 consecutive rows = one 256-byte store, no atomics
-              *reinterpret_cast<float2*>(g.row_sums + ((long long)(gc >> 5) * g.M + my_row) * 2) = make_float2(row_s, row_q);
-              row_s = row_q = 0.f;
+              float sa, sb, qa, qb;
+              unpack_f32x2(row_s2, sa, sb);
+              unpack_f32x2(row_q2, qa, qb);
+              *reinterpret_cast<float2*>(g.row_sums + ((long long)(gc >> 5) * g.M + my_row) * 2) = make_float2(sa + sb, qa + qb);
             }
+            if (kRs) row_s2 = row_q2 = 0ull;
           }
         }
         tc_fence_before();
@@ -826,40 +861,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             else tma_store_4d(&tmOut, sbuf, col0, c1, c2, c3);
             tma_store_commit();
           }
-          if (g.gn_stats != nullptr) {
+          if (kGn) {
             // GroupNorm statistics of the strip from the staged bf16 values: lane l owns the channel pair (2l, 2l+1) of
             // the strip and walks the 32 rows (one conflict-free 128-byte row read per step: the 16-byte piece holding
-            // the pair sits at ((l >> 2) ^ (r & 7))), then adds to the (instance, pair) bins with fp64 atomics. Rows are
-            // in ascending order inside the strip, so group instances form runs.
+            // the pair sits at ((l >> 2) ^ (r & 7))).
             const uint32_t vmask = __ballot_sync(0xffffffffu, my_valid);
-            const int inst_l = my_valid ? (int)(my_row / g.gn_rpi) : -1;
             const int pair_col = col0 + 2 * lane;
             const bool col_ok = pair_col < g.N && (2 * lane < g.block_n - strip);
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            int cur = -1;
             const uint8_t* sb = sbuf + (lane & 3) * 4;
-            for (int r = 0; r < 32; ++r) {
-              const int ir = __shfl_sync(0xffffffffu, inst_l, r);
-              if (!((vmask >> r) & 1u)) continue;  // warp-uniform
-              if (ir != cur) {
-                if (cur >= 0 && col_ok) {
-                  double* dst = g.gn_stats + ((long long)cur * (g.N >> 1) + (pair_col >> 1)) * 2;
-                  red_add_f64(dst, (double)(s0 + s1));
-                  red_add_f64(dst + 1, (double)(q0 + q1));
+            if (gn_acc != nullptr) {
+              // the whole tile lies in one instance: sums go to this lane quarter's shared-memory accumulators (plain
+              // read-modify-write: no other warp of the quarter owns these columns), flushed on instance change
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+              if (vmask == 0xffffffffu) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                  const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(sb + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
                 }
-                s0 = s1 = q0 = q1 = 0.f;
-                cur = ir;
-              }
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(sb + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4));
-              const float2 f = unpack_bf16(u);
-              s0 += f.x; s1 += f.y;
-              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
-            }
-            if (cur >= 0 && col_ok) {
-              if (gn_acc != nullptr) {  // the whole tile lies in `cur`: CTA-level accumulators, flushed on instance change
-                atomicAdd(gn_acc + pair_col, s0 + s1);
-                atomicAdd(gn_acc + pair_col + 1, q0 + q1);
               } else {
+                for (int r = 0; r < 32; ++r) {
+                  if (!((vmask >> r) & 1u)) continue;  // warp-uniform
+                  const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(sb + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+              }
+              if (col_ok) {
+                float2* d = reinterpret_cast<float2*>(gn_acc + pair_col);
+                float2 o = *d;
+                o.x += s0 + s1;
+                o.y += q0 + q1;
+                *d = o;
+              }
+            } else {
+              // LINEAR tile straddling group instances (low-resolution levels): rows ascend inside the strip, so the
+              // instances form runs; each run goes straight to the global fp64 bins
+              const int inst_l = my_valid ? (int)(my_row / g.gn_rpi) : -1;
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+              int cur = -1;
+              for (int r = 0; r < 32; ++r) {
+                const int ir = __shfl_sync(0xffffffffu, inst_l, r);
+                if (!((vmask >> r) & 1u)) continue;  // warp-uniform
+                if (ir != cur) {
+                  if (cur >= 0 && col_ok) {
+                    double* dst = g.gn_stats + ((long long)cur * (g.N >> 1) + (pair_col >> 1)) * 2;
+                    red_add_f64(dst, (double)(s0 + s1));
+                    red_add_f64(dst + 1, (double)(q0 + q1));
+                  }
+                  s0 = s1 = q0 = q1 = 0.f;
+                  cur = ir;
+                }
+                const float2 f = unpack_bf16(*reinterpret_cast<const uint32_t*>(sb + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+                s0 += f.x; s1 += f.y;
+                q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+              }
+              if (cur >= 0 && col_ok) {
                 double* dst = g.gn_stats + ((long long)cur * (g.N >> 1) + (pair_col >> 1)) * 2;
                 red_add_f64(dst, (double)(s0 + s1));
                 red_add_f64(dst + 1, (double)(q0 + q1));
@@ -870,7 +928,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if (lane == 0) tma_store_wait_read();
-      if (g.gn_stats != nullptr) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
+      if (kGn) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
     } else {
     int it = 0;
     for (;; ++it) {
@@ -898,14 +956,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const float* rv = nullptr;
       if (g.rowvec != nullptr && valid) rv = g.rowvec + (out_row / g.rows_per_vec) * g.ldrv;
       float* gn_acc = nullptr;
-      if (g.gn_stats != nullptr) {
+      if (kGn) {
         const int ti = tile_instance(g, t);
         if (ti >= 0) {
           if (ti != cur_inst) {
             if (cur_inst >= 0) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
             cur_inst = ti;
           }
-          gn_acc = gn_acc_base;
+          gn_acc = gn_acc_base + q * g.N;  // this lane quarter's copy
         }
       }
 
@@ -916,7 +974,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * kAccCols + ch * 32, v);
         tmem_ld_wait();
         const int col0 = t.n0 + ch * 32;
-        if (col0 < g.N) epilogue_chunk(g, v, out_row, col0, rv, valid, lane, gn_acc);  // col0 is warp-uniform
+        if (col0 < g.N) epilogue_chunk<kFeat>(g, v, out_row, col0, rv, valid, lane, gn_acc);  // col0 is warp-uniform
         __syncwarp();
       }
       tc_fence_before();
@@ -926,7 +984,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         else mbar_arrive_cluster(&tempty_bar[acc], 0);
       }
     }
-    if (g.gn_stats != nullptr) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
+    if (kGn) gn_flush(g, gn_acc_base, cur_inst, epi_tid);
       }
   }
 
@@ -937,6 +995,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (kCtas == 2) tmem_dealloc_pair<512>(tmem_base);
     else tmem_dealloc<512>(tmem_base);
   }
+}
+
+// GroupNorm-statistics producers whose natural tile (e.g. BN = 160 for N = 320) is not a multiple of 64 columns would use
+// the direct epilogue, where the column sums are a register butterfly (+35 % on the level-0 temporal conv, which has
+// little MMA time to hide it under). Up to this K they take a padded 64-column-granular tile instead so that the TMA
+// epilogue (column sums read from the staged strip) applies (measured: level-0 temporal conv +0.010 ms instead of +0.075,
+// level-1 +0.012 instead of +0.037); longer K is MMA bound and keeps the exact tile.
+static int gn_tma_max_k() {
+  static const int v = [] {
+    const char* e = getenv("TTVDM_GN_TMA_MAXK");
+    return e ? atoi(e) : 2048;
+  }();
+  return v;
 }
 
 static int pick_block_n(int N) {
@@ -952,6 +1023,19 @@ static int pick_block_n(int N) {
 }  // namespace ttvdm
 
 using namespace ttvdm;
+
+template <int kCtas, int kFeat>
+static cudaError_t launch_variant(const cudaLaunchConfig_t* cfg, const CUtensorMap& tmA, const CUtensorMap& tmA2,
+                                  const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                                  const GemmArgs& g) {
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<kCtas, kFeat>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return cudaLaunchKernelEx(cfg, gemm_kernel<kCtas, kFeat>, tmA, tmA2, tmB, tmOut, tmRes, g);
+}
 
 extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   if (int rc = ensure_init()) return rc;
@@ -978,10 +1062,14 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
                     p->gn_rows_per_inst, p->M);
     }
   }
-  if (p->ln_rowsums && (!p->ln_colsum || p->N % 32 != 0 || p->out_fp32 || (p->k1 + k2) % 32 != 0))
-    return fail(TTVDM_ERR_SHAPE, "gemm: LayerNorm fold needs ln_colsum, a bf16 output and N %% 32 == 0");
+  if (p->gn_stats_out && p->N > 2560) return fail(TTVDM_ERR_SHAPE, "gemm: gn_stats_out supports N <= 2560");
+  if (p->ln_rowsums && (!p->ln_colsum || !p->bias || p->rowvec || p->N % 32 != 0 || p->out_fp32 || (p->k1 + k2) % 32 != 0))
+    return fail(TTVDM_ERR_SHAPE, "gemm: LayerNorm fold needs ln_colsum, the folded bias, no rowvec, a bf16 output and N %% 32 == 0");
   if (p->ln_rowsums && (p->prevec || p->ln_row_add) && (p->prevec_rows <= 0 || p->prevec_mod <= 0))
     return fail(TTVDM_ERR_SHAPE, "gemm: prevec needs prevec_rows > 0 and prevec_mod > 0");
+  const int feat = p->ln_rowsums ? 1 : (p->row_sums_out ? 2 : (p->gn_stats_out ? 3 : 0));
+  if ((p->ln_rowsums != nullptr) + (p->row_sums_out != nullptr) + (p->gn_stats_out != nullptr) > 1)
+    return fail(TTVDM_ERR_SHAPE, "gemm: ln_rowsums, row_sums_out and gn_stats_out are mutually exclusive (one fusion per launch)");
   if (p->prevec && (p->ldpv % 4 != 0 || (reinterpret_cast<uintptr_t>(p->prevec) & 15)))
     return fail(TTVDM_ERR_SHAPE, "gemm: prevec must be 16 B aligned with ldpv %% 4 == 0");
 
@@ -999,7 +1087,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   // long-K GEMMs are MMA bound: they keep the deeper operand pipeline (no staging buffers) and the direct epilogue
   if (g.block_n % 64 == 0 && p->N >= 64 && (ktot_pre <= 2048 || p->geglu)) {
     want_tma = 1;
-  } else if (ktot_pre <= 640 && p->N >= 64) {
+  } else if ((ktot_pre <= 640 || (p->gn_stats_out && ktot_pre <= gn_tma_max_k())) && p->N >= 64) {
     // short-K GEMMs are epilogue / memory bound: take a 64-column-granular tile (fewest N tiles, then least padding)
     // so the TMA epilogue applies, even if that pads the last N tile
     int best = 0, best_tiles = 1 << 30;
@@ -1029,7 +1117,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     if (force_direct) g.tma_epi = 0;
   }
   // CTA-level GroupNorm accumulators ([N / 2][2] floats) live behind the operand ring / staging / resident W tile
-  const int gn_bytes = p->gn_stats_out ? ((p->N * 4 + 127) & ~127) : 0;
+  const int gn_bytes = p->gn_stats_out ? ((p->N * 16 + 127) & ~127) : 0;  // 4 copies (one per TMEM lane quarter)
   const int epi_bytes = (g.tma_epi ? kEpiWarps * kEpiBufBytes : 0) + gn_bytes;
   // B-resident schedule for short-K, many-M-tile GEMMs (the K = 320 level-0 linears): re-streaming the W tile from L2 for
   // every 128 rows makes them L2->SM bandwidth bound; pinning one N tile per CTA cuts the operand traffic per tile from
@@ -1220,12 +1308,6 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
       uint32_t box[2] = {kBlockK, (uint32_t)(g.block_n / 2)};
       if ((rc = make_tmap_bf16(&tmB, p->w, 2, dims, str, box))) return rc;
     }
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaError_t e2 = cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-      if (e2 != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e2));
-      attr2 = true;
-    }
     const int pair_tiles = ((g.m_tiles + 1) / 2) * g.n_tiles;
     const int max_pairs = g_num_sms / 2;
     const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
@@ -1242,23 +1324,33 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    le = cudaLaunchKernelEx(&cfg, gemm_kernel<2>, tmA, tmA2, tmB, tmOut, tmRes, g);
+    switch (feat) {
+      case 1: le = launch_variant<2, 1>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      case 2: le = launch_variant<2, 2>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      case 3: le = launch_variant<2, 3>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      default: le = launch_variant<2, 0>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+    }
     if (le != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm_kernel<2>: %s", cudaGetErrorString(le));
   } else {
     const size_t smem = 2048 + (size_t)g.stages * stage_b + epi_bytes + (g.b_resident ? b_res_bytes : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-      if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
     const int grid = g.b_resident ? g.ctas_per_n * g.n_tiles : (num_tiles < g_num_sms ? num_tiles : g_num_sms);
     if (g.contig) {
       const int per = g.b_resident ? g.ctas_per_n : grid;       // CTAs sharing the tile list
       const int total = g.b_resident ? g.m_tiles : num_tiles;   // tiles in that list
       g.tiles_per_cta = (total + per - 1) / per;
     }
-    gemm_kernel<1><<<grid, kNumThreads, smem, stream>>>(tmA, tmA2, tmB, tmOut, tmRes, g);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    switch (feat) {
+      case 1: le = launch_variant<1, 1>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      case 2: le = launch_variant<1, 2>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      case 3: le = launch_variant<1, 3>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+      default: le = launch_variant<1, 0>(&cfg, tmA, tmA2, tmB, tmOut, tmRes, g); break;
+    }
+    if (le != cudaSuccess) return fail(TTVDM_ERR_CUDA, "gemm_kernel<1>: %s", cudaGetErrorString(le));
   }
   TTVDM_CHECK_LAUNCH("gemm_kernel");
   return 0;

@@ -16,6 +16,7 @@ the stand-alone forward() calls; the fused sampler path has its own glue kernels
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -108,6 +109,7 @@ class AttnW:
     wv: Optional[torch.Tensor] = None
     wo: torch.Tensor = None
     bo: torch.Tensor = None
+    ln: Tuple[torch.Tensor, torch.Tensor] = None  # (gamma, beta) fp32 of the LayerNorm in front (unfused path)
 
 
 @dataclass
@@ -117,6 +119,7 @@ class FFW:
     cs1: torch.Tensor = None  # column sums of w1
     w2: torch.Tensor = None
     b2: torch.Tensor = None
+    ln: Tuple[torch.Tensor, torch.Tensor] = None  # (gamma, beta) fp32 of the LayerNorm in front (unfused path)
 
 
 @dataclass
@@ -150,20 +153,23 @@ class TfW:
     pos_b2: torch.Tensor = None
 
 
-def _fold_ln(ws: Sequence[torch.Tensor], b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, dev,
-             geglu: bool = False):
-    """LayerNorm(gamma, beta) followed by Linear(cat(ws), b)  ->  (W' bf16, bias' fp32, colsum fp32) with
-    Linear(LN(x)) = rstd * (x W'^T - mean * colsum) + bias'   (ttvdm_pack_linear; geglu: (hidden_j, gate_j) row interleave)."""
+def _fold_ln(ws: Sequence[torch.Tensor], b: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
+             beta: Optional[torch.Tensor], dev, geglu: bool = False):
+    """Linear(cat(ws), b) packed for ttvdm_gemm, optionally with the LayerNorm(gamma, beta) in front of it folded in:
+    (W' bf16, bias' fp32 or None, colsum fp32 or None) with Linear(LN(x)) = rstd * (x W'^T - mean * colsum) + bias'
+    (ttvdm_pack_linear; geglu: (hidden_j, gate_j) row interleave). gamma = None: plain repack, no fold."""
     ws = [_src(w, dev) for w in ws]
-    gamma, beta = _src(gamma, dev).to(ws[0].dtype), _src(beta, dev).to(ws[0].dtype)
+    fold = gamma is not None
+    if fold:
+        gamma, beta = _src(gamma, dev).to(ws[0].dtype), _src(beta, dev).to(ws[0].dtype)
     N, K = sum(w.shape[0] for w in ws), ws[0].shape[1]
     wf = torch.empty(N, K, dtype=BF16, device=dev)
-    bias = torch.empty(N, dtype=torch.float32, device=dev)
-    cs = torch.empty(N, dtype=torch.float32, device=dev)
+    bias = torch.empty(N, dtype=torch.float32, device=dev) if (fold or b is not None) else None
+    cs = torch.empty(N, dtype=torch.float32, device=dev) if fold else None
     row0 = 0
     for w in ws:
-        lib.pack_linear(w, wf, bias=None if b is None else _src(b, dev).to(w.dtype), gamma=gamma, beta=beta, out_bias=bias,
-                        out_colsum=cs, geglu=geglu, out_row0=row0)
+        lib.pack_linear(w, wf, bias=None if b is None else _src(b, dev).to(w.dtype), gamma=gamma if fold else None,
+                        beta=beta if fold else None, out_bias=bias, out_colsum=cs, geglu=geglu, out_row0=row0)
         row0 += w.shape[0]
     return wf, bias, cs
 
@@ -198,6 +204,10 @@ class DenoiserEngine:
         self._pool_used = 0
         self._pool_high = 0
         self.fuse_norm_stats = True  # False: standalone GroupNorm statistics pass (A/B switch for profiling / tests)
+        # LayerNorm folded into the consuming GEMM (row sums from the producer's epilogue). Built, tested and measured
+        # (profiles/r02_fusion_costs.json): on B200 the extra epilogue work costs more than the layernorm kernel it
+        # removes at every level, so it is OFF unless TTVDM_FUSE_LN=1 — the weights are packed accordingly.
+        self.fuse_layernorm = os.environ.get("TTVDM_FUSE_LN", "0") == "1"
         self._pack(model)
 
     # ============================================================================================ packing
@@ -235,7 +245,8 @@ class DenoiserEngine:
 
         def attn(prefix: str, cross: bool, ln: str) -> AttnW:
             a = AttnW()
-            gamma, beta = g(ln + ".weight"), g(ln + ".bias")
+            gamma, beta = (g(ln + ".weight"), g(ln + ".bias")) if self.fuse_layernorm else (None, None)
+            a.ln = (_f32(g(ln + ".weight"), dev), _f32(g(ln + ".bias"), dev))
             if cross:
                 a.wq, a.w_b, a.w_cs = _fold_ln([g(prefix + ".to_q.weight")], None, gamma, beta, dev)
                 a.wk = _bf(g(prefix + ".to_k.weight"), dev)
@@ -249,8 +260,10 @@ class DenoiserEngine:
         def ff(prefix: str, ln: str) -> FFW:
             f = FFW()
             # GEGLU rows interleaved (hidden_j, gate_j) by the repack kernel: weights, bias and column sums stay aligned
-            f.w1, f.b1, f.cs1 = _fold_ln([g(prefix + ".net.0.proj.weight")], g(prefix + ".net.0.proj.bias"),
-                                         g(ln + ".weight"), g(ln + ".bias"), dev, geglu=True)
+            gamma, beta = (g(ln + ".weight"), g(ln + ".bias")) if self.fuse_layernorm else (None, None)
+            f.ln = (_f32(g(ln + ".weight"), dev), _f32(g(ln + ".bias"), dev))
+            f.w1, f.b1, f.cs1 = _fold_ln([g(prefix + ".net.0.proj.weight")], g(prefix + ".net.0.proj.bias"), gamma, beta, dev,
+                                         geglu=True)
             f.w2, f.b2 = _bf(g(prefix + ".net.2.weight"), dev), _f32(g(prefix + ".net.2.bias"), dev)
             return f
 
@@ -441,6 +454,12 @@ class DenoiserEngine:
                  rows_per_vec=rows_per_vec, ldrv=ldrv, s0=s0, res1=res1, s1=s1, res2=res2, s2=s2, **kw)
         return out
 
+    def _ln(self, x, gb, *, rows, C, addvec=None, F=0, S=0, sum_out=None, out=None):
+        if out is None:
+            out = self._empty(rows, C)
+        lib.layernorm(x, out, gb[0], gb[1], rows=rows, C=C, addvec=addvec, F=F, S=S, sum_out=sum_out)
+        return out
+
     def _gn(self, x, gamma, beta, *, rows, rows_per_inst, eps, silu, x2=None):
         """GroupNorm(32) (+SiLU, + channel concat with x2). Sources whose producing GEMM left per-pair sums for this
         instance size (tensor.gn_stats) skip the statistics pass."""
@@ -479,24 +498,26 @@ class DenoiserEngine:
         semb = self._linear(h2, self.ae_w2, M=R, bias=self.ae_b2, res1=emb, act=1)
         return self._linear(semb, self.temb_w, M=R, bias=self.temb_b, out_fp32=True)
 
-    def context_kv(self, ehs: torch.Tensor) -> List[List[Tuple[torch.Tensor, ...]]]:
+    def context_kv(self, ehs: torch.Tensor, out: Optional[list] = None) -> List[List[Tuple[torch.Tensor, ...]]]:
         """Cross-attention K/V of the (constant) context for every transformer layer: computed once per video instead of
         per frame / per pixel (reference: svd/unet_spatio_temporal_condition.py:452 repeat_interleave,
         svd/diffusion_arch/transformer_temporal.py:316-319 broadcast). ehs [B, L, D] -> per transformer, per layer
-        (k_s, v_s, k_t, v_t), each bf16 [B, L, C]."""
+        (k_s, v_s, k_t, v_t), each bf16 [B, L, C]. `out`: a previous result of the same shape to overwrite in place (the
+        captured step graph keeps reading the same buffers for the next video)."""
         B, L, D = ehs.shape
         x = _bf(ehs.reshape(B * L, D), self.device)
-        out = []
-        for t in self.all_transformers():
+        res = []
+        for ti, t in enumerate(self.all_transformers()):
             per_layer = []
-            for ly in t.layers:
-                ks = self._linear(x, ly.s_attn2.wk, M=B * L)
-                vs = self._linear(x, ly.s_attn2.wv, M=B * L)
-                kt = self._linear(x, ly.t_attn2.wk, M=B * L)
-                vt = self._linear(x, ly.t_attn2.wv, M=B * L)
+            for li, ly in enumerate(t.layers):
+                old = out[ti][li] if out is not None else (None, None, None, None)
+                ks = self._linear(x, ly.s_attn2.wk, M=B * L, out=old[0])
+                vs = self._linear(x, ly.s_attn2.wv, M=B * L, out=old[1])
+                kt = self._linear(x, ly.t_attn2.wk, M=B * L, out=old[2])
+                vt = self._linear(x, ly.t_attn2.wv, M=B * L, out=old[3])
                 per_layer.append((ks, vs, kt, vt))
-            out.append(per_layer)
-        return out
+            res.append(per_layer)
+        return res
 
     def _ensure_pos_emb(self, F: int) -> None:
         """time_pos_embed(time_proj(arange(F))) is input independent (transformer_temporal.py:328-339): once. So is its
@@ -509,9 +530,10 @@ class DenoiserEngine:
             lib.sinusoid(frames, ts, n=F, dim=t.C)
             h = self._linear(ts, t.pos_w1, M=F, bias=t.pos_b1, act=1)
             t.pos_emb = self._linear(h, t.pos_w2, M=F, bias=t.pos_b2, out_fp32=True)
-            pe = _bf(t.pos_emb, self.device)
-            for ly in t.layers:
-                ly.pos_prevec = self._linear(pe, ly.t_ff_in.w1, M=F, out_fp32=True)
+            if self.fuse_layernorm:
+                pe = _bf(t.pos_emb, self.device)
+                for ly in t.layers:
+                    ly.pos_prevec = self._linear(pe, ly.t_ff_in.w1, M=F, out_fp32=True)
         self._pos_cache = {F: True}
         self._pos_rep = {}
 
@@ -556,7 +578,61 @@ class DenoiserEngine:
                            res2=out_res2, s2=out_s2, gn_rpi=S)
 
     def _transformer(self, t: TfW, x, kv, *, B, F, H, W, n_ctx, batch_offset):
-        """TransformerSpatioTemporalModel.forward (svd/diffusion_arch/transformer_temporal.py:276-381).
+        """TransformerSpatioTemporalModel.forward (svd/diffusion_arch/transformer_temporal.py:276-381)."""
+        if self.fuse_layernorm:
+            return self._transformer_ln_folded(t, x, kv, B=B, F=F, H=H, W=W, n_ctx=n_ctx, batch_offset=batch_offset)
+        S = H * W
+        rows = B * F * S
+        C = t.C
+        scale = 0.125
+        y = self._gn(x, t.gn_g, t.gn_b, rows=rows, rows_per_inst=S, eps=1e-6, silu=False)
+        h = self._linear(y, t.w_in, M=rows, bias=t.b_in)
+        qkv = q = gg = hm = None
+        for li, (ly, (ks, vs, kt, vt)) in enumerate(zip(t.layers, kv)):
+            L = ks.shape[0] // n_ctx
+            # ---- spatial BasicTransformerBlock
+            y = self._ln(h, ly.s_attn1.ln, rows=rows, C=C, out=y)
+            qkv = self._linear(y, ly.s_attn1.wqkv, M=rows, out=qkv)
+            o = y  # reuse
+            lib.attn_spatial(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, n_img=B * F,
+                             heads=t.heads, seq=S, scale=scale)
+            self._linear(o, ly.s_attn1.wo, M=rows, bias=ly.s_attn1.bo, res1=h, out=h)
+            y = self._ln(h, ly.s_attn2.ln, rows=rows, C=C, out=y)
+            q = self._linear(y, ly.s_attn2.wq, M=rows, out=q)
+            lib.attn_cross(q, ks, vs, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
+                           temporal=False, batch_offset=batch_offset, scale=scale)
+            self._linear(y, ly.s_attn2.wo, M=rows, bias=ly.s_attn2.bo, res1=h, out=h)
+            y = self._ln(h, ly.s_ff.ln, rows=rows, C=C, out=y)
+            gg = self._linear(y, ly.s_ff.w1, M=rows, bias=ly.s_ff.b1, geglu=True, out=gg)
+            self._linear(gg, ly.s_ff.w2, M=rows, bias=ly.s_ff.b2, res1=h, out=h)  # h == x_spatial
+            # ---- TemporalBasicTransformerBlock on (h + frame positional embedding); rows stay (b, f, s)
+            if hm is None:
+                hm = self._empty(rows, C)
+            y = self._ln(h, ly.t_ff_in.ln, rows=rows, C=C, addvec=t.pos_emb, F=F, S=S, sum_out=hm, out=y)
+            gg = self._linear(y, ly.t_ff_in.w1, M=rows, bias=ly.t_ff_in.b1, geglu=True, out=gg)
+            self._linear(gg, ly.t_ff_in.w2, M=rows, bias=ly.t_ff_in.b2, res1=hm, out=hm)
+            y = self._ln(hm, ly.t_attn1.ln, rows=rows, C=C, out=y)
+            qkv = self._linear(y, ly.t_attn1.wqkv, M=rows, out=qkv)
+            lib.attn_temporal(qkv, qkv[:, C:], qkv[:, 2 * C:], y, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, B=B, F=F, S=S,
+                              heads=t.heads, scale=scale)
+            self._linear(y, ly.t_attn1.wo, M=rows, bias=ly.t_attn1.bo, res1=hm, out=hm)
+            y = self._ln(hm, ly.t_attn2.ln, rows=rows, C=C, out=y)
+            q = self._linear(y, ly.t_attn2.wq, M=rows, out=q)
+            lib.attn_cross(q, kt, vt, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
+                           temporal=True, batch_offset=batch_offset, scale=scale)
+            self._linear(y, ly.t_attn2.wo, M=rows, bias=ly.t_attn2.bo, res1=hm, out=hm)
+            y = self._ln(hm, ly.t_ff.ln, rows=rows, C=C, out=y)
+            gg = self._linear(y, ly.t_ff.w1, M=rows, bias=ly.t_ff.b1, geglu=True, out=gg)
+            # AlphaBlender fused: a*h + (1-a)*(ff + hm)
+            a = t.alpha
+            self._linear(gg, ly.t_ff.w2, M=rows, bias=ly.t_ff.b2, s0=1.0 - a, res1=hm, s1=1.0 - a, res2=h, s2=a, out=h)
+        # ---- proj_out + input residual (its epilogue leaves the GroupNorm sums of the next ResBlock)
+        if hm is None:
+            hm = self._empty(rows, C)
+        return self._linear(h, t.w_out, M=rows, bias=t.b_out, res1=x, out=hm, gn_rpi=S)
+
+    def _transformer_ln_folded(self, t: TfW, x, kv, *, B, F, H, W, n_ctx, batch_offset):
+        """TransformerSpatioTemporalModel.forward with every LayerNorm folded into its consumer (TTVDM_FUSE_LN=1).
         No LayerNorm kernel runs: each of the 7 LayerNorms per layer is folded into the GEMM that consumes it (folded
         weights + epilogue scale from the row sums the producing GEMM's epilogue accumulated), and `hidden + frame
         positional embedding` (:356) is never materialised — the embedding enters the statistics (rs_add), the ff_in

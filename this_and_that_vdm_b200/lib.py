@@ -198,6 +198,11 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 _profile: Optional[list] = None
 
 
+def profiling() -> bool:
+    """True while start_profile() is active (per-call CUDA events are not graph capturable: callers stay eager)."""
+    return _profile is not None
+
+
 def start_profile() -> None:
     global _profile
     _profile = []

@@ -13,6 +13,7 @@ Schedule of one VGL step on one GPU holding B_local (1 or 2) of the CFG pair's s
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -22,11 +23,28 @@ from .engine import PAD_IN, DenoiserEngine
 
 
 class FusedDenoiser:
-    def __init__(self, unet_engine: DenoiserEngine, controlnet_engine: Optional[DenoiserEngine] = None):
+    """use_graph (default: env TTVDM_STEP_GRAPH, on): the network part of a step (UNet encoder + mid, GestureNet, zero
+    convs, UNet decoder: ~1000 launches) is captured ONCE into a CUDA graph whose private memory pool is the static
+    activation arena, and replayed for every Euler step of every video of the same shape: per step the host then issues a
+    small copy (the step's timestep-embedding rows into a static buffer), the prepare kernel, ONE graph launch and the
+    Euler kernel — no allocation, no per-kernel launch cost. Everything the graph reads sits at fixed addresses: model
+    input, timestep rows, context K/V (overwritten in place per video), frame positional embeddings, weights."""
+
+    def __init__(self, unet_engine: DenoiserEngine, controlnet_engine: Optional[DenoiserEngine] = None,
+                 use_graph: Optional[bool] = None):
         self.unet = unet_engine
         self.cn = controlnet_engine
         self.device = unet_engine.device
         self._prepared = False
+        if use_graph is None:
+            use_graph = os.environ.get("TTVDM_STEP_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph)
+        self._graphs = {}      # key -> (graph, eps output)
+        self._static = {}      # key -> dict of static buffers (x_in, temb_u, temb_c, kv_u, kv_c)
+        self._warm = {}        # key -> eager steps run so far (pool sizes are learned before capture)
+
+    def _key(self):
+        return (self.B, self.b_local, self.batch_offset, self.F, self.h, self.w, self.cn is not None)
 
     def prepare(self, encoder_hidden_states: torch.Tensor, image_latents: torch.Tensor,
                 added_time_ids: torch.Tensor, sigmas: torch.Tensor, timesteps: torch.Tensor,
@@ -56,18 +74,47 @@ class FusedDenoiser:
         # all steps' embeddings at once: rows ordered (step, local batch element)
         t_rows = timesteps.to(dev, torch.float32).reshape(n, 1).expand(n, self.b_local).reshape(-1).contiguous()
         id_rows = ids[sl].unsqueeze(0).expand(n, self.b_local, ids.shape[1]).reshape(n * self.b_local, -1).contiguous()
+        if self.cn is not None and self.cond is None:
+            raise ValueError("controlnet_cond is required when a ControlNet is given")
+        st = self._static.setdefault(self._key(), {})
+        L = encoder_hidden_states.shape[1]
+        if st.get("L") != L:  # context length changed (use_text on / off): the K/V buffers and the graph are stale
+            st.clear()
+            self._graphs.pop(self._key(), None)
+            self._warm.pop(self._key(), None)
+            st["L"] = L
         self.unet._ensure_pos_emb(num_frames)
         self.temb_u = self.unet.time_embeddings(t_rows, id_rows)
-        self.kv_u = self.unet.context_kv(encoder_hidden_states.to(dev))
+        st["kv_u"] = self.kv_u = self.unet.context_kv(encoder_hidden_states.to(dev), out=st.get("kv_u"))
         if self.cn is not None:
-            if self.cond is None:
-                raise ValueError("controlnet_cond is required when a ControlNet is given")
             self.cn._ensure_pos_emb(num_frames)
             self.temb_c = self.cn.time_embeddings(t_rows, id_rows)
-            self.kv_c = self.cn.context_kv(encoder_hidden_states.to(dev))
+            st["kv_c"] = self.kv_c = self.cn.context_kv(encoder_hidden_states.to(dev), out=st.get("kv_c"))
         rows = self.b_local * num_frames * height * width
-        self.x_in = torch.empty(rows, PAD_IN, dtype=torch.bfloat16, device=dev)
+        if "x_in" not in st:
+            st["x_in"] = torch.empty(rows, PAD_IN, dtype=torch.bfloat16, device=dev)
+            st["temb_u"] = torch.empty(self.b_local, self.temb_u.shape[1], dtype=torch.float32, device=dev)
+            if self.cn is not None:
+                st["temb_c"] = torch.empty(self.b_local, self.temb_c.shape[1], dtype=torch.float32, device=dev)
+        self.x_in = st["x_in"]
         self._prepared = True
+
+    # ---- the network part of a step: reads only static buffers (graph capturable)
+    def _network(self, temb_u, temb_c, cond_scale: float) -> torch.Tensor:
+        F, h, w, bl = self.F, self.h, self.w, self.b_local
+        kw = dict(B=bl, F=F, n_ctx=self.B, batch_offset=self.batch_offset)
+        self.unet.begin_step()
+        if self.cn is not None:
+            self.cn.begin_step()
+        x, skips, dims, ti = self.unet.encode(self.x_in, temb_u, self.kv_u, H=h, W=w, **kw)
+        hl, wl = dims[-1]
+        x, ti = self.unet.middle(x, temb_u, self.kv_u, ti, H=hl, W=wl, **kw)
+        if self.cn is not None:
+            cx, cskips, _, cti = self.cn.encode(self.x_in, temb_c, self.kv_c, H=h, W=w, **kw)
+            cx, _ = self.cn.middle(cx, temb_c, self.kv_c, cti, H=hl, W=wl, **kw)
+            # the down path is finished, so the residuals can be accumulated into the skip tensors in place
+            self.cn.zero_convs(cskips, cx, [cond_scale] * (len(cskips) + 1), into=skips, mid_into=x, n_img=bl * F)
+        return self.unet.decode(x, skips, temb_u, self.kv_u, ti, H=hl, W=wl, **kw)
 
     def predict(self, i: int, latents: torch.Tensor) -> torch.Tensor:
         """Noise prediction of step i for the local sequences: fp32 [b_local*F*h*w, 4] channels-last.
@@ -76,21 +123,46 @@ class FusedDenoiser:
         F, h, w, bl = self.F, self.h, self.w, self.b_local
         lib.sampler_prepare(latents, self.image_latents, self.cond, self.x_in, c_pad=PAD_IN, B_local=bl,
                             batch_offset=self.batch_offset, F=F, h=h, w=w, sigma=self.sigmas[i])
-        kw = dict(B=bl, F=F, n_ctx=self.B, batch_offset=self.batch_offset)
-        self.unet.begin_step()
-        if self.cn is not None:
-            self.cn.begin_step()
         temb_u = self.temb_u[i * bl:(i + 1) * bl]
-        x, skips, dims, ti = self.unet.encode(self.x_in, temb_u, self.kv_u, H=h, W=w, **kw)
-        hl, wl = dims[-1]
-        x, ti = self.unet.middle(x, temb_u, self.kv_u, ti, H=hl, W=wl, **kw)
+        temb_c = self.temb_c[i * bl:(i + 1) * bl] if self.cn is not None else None
+        if not self.use_graph or self.device.type != "cuda" or lib.profiling():
+            return self._network(temb_u, temb_c, self.cond_scale)
+        key = self._key()
+        st = self._static[key]
+        st["temb_u"].copy_(temb_u)
         if self.cn is not None:
-            temb_c = self.temb_c[i * bl:(i + 1) * bl]
-            cx, cskips, _, cti = self.cn.encode(self.x_in, temb_c, self.kv_c, H=h, W=w, **kw)
-            cx, _ = self.cn.middle(cx, temb_c, self.kv_c, cti, H=hl, W=wl, **kw)
-            # the down path is finished, so the residuals can be accumulated into the skip tensors in place
-            self.cn.zero_convs(cskips, cx, [self.cond_scale] * (len(cskips) + 1), into=skips, mid_into=x, n_img=bl * F)
-        return self.unet.decode(x, skips, temb_u, self.kv_u, ti, H=hl, W=wl, **kw)
+            st["temb_c"].copy_(temb_c)
+        gkey = (key, self.cond_scale)
+        ent = self._graphs.get(key)
+        if ent is not None and ent[2] != self.cond_scale:
+            # the conditioning scale is baked into the captured zero-conv launches; a per-step schedule of scales
+            # (control_guidance_start / end) runs eagerly instead of re-capturing every step
+            return self._network(st["temb_u"], st.get("temb_c"), self.cond_scale)
+        if ent is None:
+            warm = self._warm.get(gkey, 0)
+            if warm < 2:
+                # two eager steps first: the statistics pools learn their size, every lazy initialisation has happened
+                self._warm[gkey] = warm + 1
+                return self._network(st["temb_u"], st.get("temb_c"), self.cond_scale)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                eps = self._network(st["temb_u"], st.get("temb_c"), self.cond_scale)
+            ent = (graph, eps, self.cond_scale)
+            self._graphs[key] = ent
+        ent[0].replay()
+        return ent[1]
+
+    @staticmethod
+    def cached(unet_engine: DenoiserEngine, controlnet_engine: Optional[DenoiserEngine] = None) -> "FusedDenoiser":
+        """One FusedDenoiser per (UNet engine, GestureNet engine) pair, so the captured step graphs and their static
+        buffers survive across pipeline calls."""
+        cache = unet_engine.__dict__.setdefault("_fused_denoisers", {})
+        key = id(controlnet_engine) if controlnet_engine is not None else 0
+        den = cache.get(key)
+        if den is None or den.cn is not controlnet_engine:
+            den = cache[key] = FusedDenoiser(unet_engine, controlnet_engine)
+        return den
 
     def euler_update(self, i: int, latents: torch.Tensor, eps_u: torch.Tensor, eps_c: torch.Tensor) -> None:
         lib.sampler_euler_step(latents, eps_u, eps_c, self.guidance, ld_eps=eps_u.shape[1] if eps_u.dim() == 2 else 4,

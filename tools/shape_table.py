@@ -64,6 +64,58 @@ def row_linear(M, N, K, *, geglu=False, res=0, per_step=0, note=""):
             "note": note}
 
 
+def row_fusion_variants(M, C, S, F=14):
+    """Cost of the epilogue fusions in isolation, L-level shapes: producer C x C (+res) plain / + LayerNorm row sums /
+    + GroupNorm pair sums; consumer qkv and GEGLU with the LayerNorm fold; 3x3 conv and temporal conv with GroupNorm sums."""
+    rows = []
+    a, w, b, r1 = rnd(M, C), rnd(C, C, scale=C ** -0.5), torch.randn(C, device=DEV), rnd(M, C)
+    out = torch.empty(M, C, dtype=BF, device=DEV)
+    rs = torch.empty(C // 32, M, 2, dtype=torch.float32, device=DEV)
+    st = torch.zeros((M // S) * C, dtype=torch.float64, device=DEV)
+    base = time_it(lambda: lib.gemm(a, w, out, M=M, N=C, k1=C, bias=b, res1=r1))
+    t_rs = time_it(lambda: lib.gemm(a, w, out, M=M, N=C, k1=C, bias=b, res1=r1, row_sums_out=rs))
+    t_gn = time_it(lambda: lib.gemm(a, w, out, M=M, N=C, k1=C, bias=b, res1=r1, gn_stats_out=st, gn_rows_per_inst=S))
+    rows.append({"op": "CxC+res: plain / +row_sums / +gn_stats", "M": M, "N": C, "K": C, "plain_ms": round(base, 4),
+                 "row_sums_ms": round(t_rs, 4), "gn_stats_ms": round(t_gn, 4)})
+    for N, geglu in ((3 * C, False), (8 * C, True)):
+        wq, bq, cs = rnd(N, C, scale=C ** -0.5), torch.randn(N, device=DEV), torch.randn(N, device=DEV)
+        o2 = torch.empty(M, N // 2 if geglu else N, dtype=BF, device=DEV)
+        base = time_it(lambda: lib.gemm(a, wq, o2, M=M, N=N, k1=C, bias=bq, geglu=geglu))
+        t_ln = time_it(lambda: lib.gemm(a, wq, o2, M=M, N=N, k1=C, bias=bq, geglu=geglu, ln_rowsums=rs, ln_colsum=cs))
+        rows.append({"op": f"{'GEGLU' if geglu else 'qkv'}: plain / +LayerNorm fold", "M": M, "N": N, "K": C,
+                     "plain_ms": round(base, 4), "ln_fold_ms": round(t_ln, 4)})
+        del o2, wq
+    n, H = M // S, int(S ** 0.5 * (9 / 16) ** 0.5 + 0.5)
+    Wd = S // H
+    if H * Wd == S:
+        x, wk = rnd(n, H, Wd, C), rnd(C, 9 * C, scale=(9 * C) ** -0.5)
+        base = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_CONV3X3, n_img=n, H=H, W=Wd, bias=b))
+        t4 = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_CONV3X3, n_img=n, H=H, W=Wd, bias=b,
+                                      gn_stats_out=st, gn_rows_per_inst=S))
+        t5 = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_CONV3X3, n_img=n, H=H, W=Wd, bias=b,
+                                      gn_stats_out=st, gn_rows_per_inst=F * S))
+        rows.append({"op": "conv3x3: plain / +gn_stats 4-D / 5-D", "M": M, "N": C, "K": 9 * C, "plain_ms": round(base, 4),
+                     "gn4_ms": round(t4, 4), "gn5_ms": round(t5, 4)})
+        del wk
+    B = n // F
+    x, wk = rnd(B, F, S, C), rnd(C, 3 * C, scale=(3 * C) ** -0.5)
+    base = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=b, res1=r1))
+    t4 = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=b, res1=r1,
+                                  gn_stats_out=st, gn_rows_per_inst=S))
+    t5 = time_it(lambda: lib.gemm(x, wk, out, M=M, N=C, k1=C, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=b, res1=r1,
+                                  gn_stats_out=st, gn_rows_per_inst=F * S))
+    rows.append({"op": "tconv3+res: plain / +gn_stats 4-D / 5-D", "M": M, "N": C, "K": 3 * C, "plain_ms": round(base, 4),
+                 "gn4_ms": round(t4, 4), "gn5_ms": round(t5, 4)})
+    gm, bt = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    ws = torch.empty((M // S) * 64, dtype=torch.float64, device=DEV)
+    y = torch.empty_like(out)
+    t_full = time_it(lambda: lib.groupnorm(out, y, ws, gm, bt, c1=C, rows=M, rows_per_inst=S, eps=1e-6, silu=True))
+    t_app = time_it(lambda: lib.groupnorm(out, y, None, gm, bt, c1=C, rows=M, rows_per_inst=S, eps=1e-6, silu=True, pstats1=st))
+    rows.append({"op": "groupnorm: stats+apply / apply only (producer sums)", "M": M, "N": C, "K": 0,
+                 "full_ms": round(t_full, 4), "apply_only_ms": round(t_app, 4)})
+    return rows
+
+
 def row_conv(n, H, W, Ci, Co, *, per_step=0):
     x, wk, b = rnd(n, H, W, Ci), rnd(Co, 9 * Ci, scale=(9 * Ci) ** -0.5), torch.randn(Co, device=DEV)
     tv = torch.randn(2, Co, device=DEV)
@@ -159,6 +211,8 @@ def main():
     ]
     if quick:
         jobs = jobs[:3] + jobs[17:18]
+    if "--fusions" in sys.argv:
+        jobs = []
     table = []
     for j in jobs:
         try:
@@ -169,6 +223,20 @@ def main():
             traceback.print_exc()
             print("ROW", json.dumps({"error": str(e)[:200]}), flush=True)
         torch.cuda.empty_cache()
+    if "--fusions" in sys.argv:
+        table = []
+        for M, C, S in ((n * S0, 320, S0), (n * S1, 640, S1), (n * S2, 1280, S2)):
+            try:
+                for r in row_fusion_variants(M, C, S):
+                    table.append(r)
+                    print("ROW", json.dumps(r), flush=True)
+            except Exception:  # noqa: BLE001
+                traceback.print_exc()
+            torch.cuda.empty_cache()
+        out = Path(__file__).resolve().parents[1] / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        (out / "shape_table_fusions.json").write_text(json.dumps({"device": torch.cuda.get_device_name(0), "rows": table}, indent=1))
+        return
     try:
         for r in row_norms(n * S0, 320, S0) + row_norms(n * S1, 640, S1):
             table.append(r)
