@@ -48,6 +48,7 @@ constexpr int kD = 64;        // head dim
 constexpr int kKV = 4;        // K/V ring depth
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kAttnThreads = 128 + 128 * kQTiles;  // 4 service warps + 4 softmax warps per Q tile
+constexpr int kAttnPolyDefault = 3;  // of every 8 column pairs (see attn_flash_kernel)
 constexpr int kAttnSmem = kTileBytes * (2 * kQTiles + 2 * kKV) + 512;
 // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,320)  O_1 [320,384)  P_0 [384,448)  P_1 [448,512)
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
@@ -87,6 +88,31 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// exp2 of two exponents (x <= ~8) WITHOUT the MUFU: Cody-Waite split on the FMA pipe in packed f32x2 arithmetic.
+// t = x + 1.5 * 2^23 leaves n = round(x) in the low mantissa bits of t; f = x - n in [-0.5, 0.5]; 2^f by a degree-3
+// minimax polynomial (relative error 7.5e-5, far below the 2^-9 of the bf16 rounding P gets anyway); the result is
+// the polynomial's bit pattern with n added to the exponent field (one IMAD per element). x is clamped at -126 first
+// (masked keys are -inf; a finite key may sit hundreds of units below the row maximum).
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, float& r1) {
+  const uint64_t x2 = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = add_f32x2(x2, pack_f32x2(12582912.f, 12582912.f));
+  const uint64_t n = add_f32x2(t, pack_f32x2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f32x2(n, pack_f32x2(-1.f, -1.f), x2);
+  uint64_t q = fma_f32x2(f, pack_f32x2(0.055171459913253784f, 0.055171459913253784f),
+                         pack_f32x2(0.2426108568906784f, 0.2426108568906784f));
+  q = fma_f32x2(q, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma_f32x2(q, f, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+  float q0, q1, t0, t1;
+  unpack_f32x2(q, q0, q1);
+  unpack_f32x2(t, t0, t1);
+  r0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// kPoly of every 8 column pairs take their exponential on the FMA pipe (exp2_poly_pair), the rest on the MUFU: the
+// softmax of two 128 x 128 tiles is 2048 MUFU cycles per KV tile on one SM (16 results per clock) against 1024 cycles of
+// tensor-pipe work, so the MUFU is what bounds the kernel at d = 64 unless part of the exponentials leaves it.
+template <int kPoly>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
@@ -330,19 +356,29 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         m_used = m_new;
         const float ms = (m_used == -INFINITY) ? 0.f : m_used * c2;
         TR(4);
-        // ---- probabilities: bf16 pairs (P column c = keys 2c, 2c+1), row sum
-        float sum0 = 0.f, sum1 = 0.f;
+        // ---- probabilities: bf16 pairs (P column c = keys 2c, 2c+1), row sum (packed f32x2 scale / sum)
+        const uint64_t c22 = pack_f32x2(c2, c2), nms2 = pack_f32x2(-ms, -ms);
+        uint64_t sum_a = pack_f32x2(0.f, 0.f), sum_b = sum_a;
         uint32_t pk[2][32];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[cc][i]), c2, -ms));  // exp2(-inf) = 0 for masked keys
-            const float p1 = ex2(fmaf(__uint_as_float(v[cc][i + 1]), c2, -ms));
-            sum0 += p0;
-            sum1 += p1;
+            float x0, x1, p0, p1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[cc][i]), __uint_as_float(v[cc][i + 1])), c22, nms2), x0, x1);
+            // a ragged (masked) KV tile is rare and CTA-uniform: it keeps every exponential on the MUFU
+            if (((i >> 1) & 7) < kPoly && !masked) {
+              exp2_poly_pair(x0, x1, p0, p1);
+            } else {
+              p0 = ex2(x0);  // exp2(-inf) = 0 for masked keys
+              p1 = ex2(x1);
+            }
+            const uint64_t p2 = pack_f32x2(p0, p1);
+            if (i & 2) sum_b = add_f32x2(sum_b, p2); else sum_a = add_f32x2(sum_a, p2);
             pk[cc >> 1][(cc & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
           }
+        float sum0, sum1;
+        unpack_f32x2(add_f32x2(sum_a, sum_b), sum0, sum1);
         l_run += sum0 + sum1;
         TR(5);
         if (j > 0) {
@@ -406,11 +442,19 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     if ((rc = make_tmap_bf16(&tmK, k, 2, dims, strk, box))) return rc;
     if ((rc = make_tmap_bf16(&tmV, v, 2, dims, strv, box))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnArgs);
+  static const Kern kerns[5] = {attn_flash_kernel<0>, attn_flash_kernel<1>, attn_flash_kernel<2>, attn_flash_kernel<3>,
+                                attn_flash_kernel<4>};
+  static int poly = -1;  // column pairs of every 8 whose exponential runs on the FMA pipe (TTVDM_ATTN_POLY: A/B runs)
+  if (poly < 0) {
+    const char* e = getenv("TTVDM_ATTN_POLY");
+    int v = e ? atoi(e) : kAttnPolyDefault;
+    if (v < 0 || v > 4) v = kAttnPolyDefault;
+    for (int i = 0; i < 5; ++i) {
+      cudaError_t ce = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (ce != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    }
+    poly = v;
   }
   AttnArgs ga = g;
   ga.units = units;
@@ -423,7 +467,7 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = (int)(works < n_sm ? works : n_sm);  // persistent: one CTA per SM
-  attn_flash_kernel<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, ga);
+  kerns[poly]<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, ga);
   TTVDM_CHECK_LAUNCH("attn_flash_kernel");
   return 0;
 }

@@ -176,8 +176,18 @@ def init(device: Optional[int] = None) -> None:
         _inited_devices.add(dev)
 
 
+_graph_launches = 0
+
+
 def launch_count() -> int:
-    return int(load().ttvdm_launch_count())
+    """Kernels of this library enqueued so far: direct launches (counted inside the library) plus the kernel nodes of
+    every CUDA-graph replay reported through add_graph_launches()."""
+    return int(load().ttvdm_launch_count()) + _graph_launches
+
+
+def add_graph_launches(n: int) -> None:
+    global _graph_launches
+    _graph_launches += int(n)
 
 
 def destroy() -> None:

@@ -146,11 +146,14 @@ class FusedDenoiser:
                 return self._network(st["temb_u"], st.get("temb_c"), self.cond_scale)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            n0 = lib.launch_count()
             with torch.cuda.graph(graph):
                 eps = self._network(st["temb_u"], st.get("temb_c"), self.cond_scale)
-            ent = (graph, eps, self.cond_scale)
+            ent = (graph, eps, self.cond_scale, lib.launch_count() - n0)  # kernel nodes of this library in the graph
+            lib.add_graph_launches(-ent[3])  # the capture itself launched nothing
             self._graphs[key] = ent
         ent[0].replay()
+        lib.add_graph_launches(ent[3])
         return ent[1]
 
     @staticmethod

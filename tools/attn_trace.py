@@ -29,3 +29,26 @@ for cls, label in enumerate(["MMA", "T0", "T1"]):
 ends = [(x >> 8) - base for x in t[1] if x and (x & 255) == 6]
 if len(ends) > 60:
     print("cycles per KV tile (tile 0 softmax, steady state): %.0f" % ((ends[60] - ends[20]) / 40.0))
+# ---- per-phase averages of the softmax thread of each Q tile over the steady state (KV tiles 20..60 of the trace)
+for cls, label in ((1, "T0"), (2, "T1")):
+    ev = [((x >> 8) - base, x & 255) for x in t[cls] if x]
+    seg = {}
+    last = None
+    n6 = 0
+    for c, tag in ev:
+        if tag == 6:
+            n6 += 1
+        if last is not None and 20 <= n6 <= 60:
+            seg.setdefault((last[1], tag), []).append(c - last[0])
+        last = (c, tag)
+    print(label, "phase averages:", "  ".join("%s->%s %.0f" % (names.get(a, hex(a)), names.get(b, hex(b)), sum(v) / len(v))
+                                             for (a, b), v in sorted(seg.items())))
+ev = [((x >> 8) - base, x & 255) for x in t[0] if x]
+seg = {}
+last = None
+for c, tag in ev[200:1000]:
+    if last is not None:
+        seg.setdefault((last[1], tag), []).append(c - last[0])
+    last = (c, tag)
+print("MMA issuer phase averages:", "  ".join("%s->%s %.0f(n=%d)" % (names.get(a, hex(a)), names.get(b, hex(b)), sum(v) / len(v), len(v))
+                                           for (a, b), v in sorted(seg.items())))

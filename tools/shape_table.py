@@ -213,6 +213,8 @@ def main():
         jobs = jobs[:3] + jobs[17:18]
     if "--fusions" in sys.argv:
         jobs = []
+    if "--attn" in sys.argv:
+        jobs = jobs[17:]
     table = []
     for j in jobs:
         try:
@@ -236,6 +238,8 @@ def main():
         out = Path(__file__).resolve().parents[1] / "gpurun_out"
         out.mkdir(exist_ok=True)
         (out / "shape_table_fusions.json").write_text(json.dumps({"device": torch.cuda.get_device_name(0), "rows": table}, indent=1))
+        return
+    if "--attn" in sys.argv:
         return
     try:
         for r in row_norms(n * S0, 320, S0) + row_norms(n * S1, 640, S1):
