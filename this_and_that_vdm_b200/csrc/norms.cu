@@ -93,6 +93,12 @@ gn_stats_kernel(GnSrc s1, GnSrc s2, int C, int rows_per_inst, int rows_per_cta, 
 // `sums` (group sums of the sources that went through gn_stats_kernel; NULL if none did) plus, per source, the
 // per-(instance, channel pair) sums the producing GEMM's epilogue accumulated (ttvdm_gemm gn_stats_out) — folded into
 // the 32 group sums by every CTA (C / 2 <= 2560 doubles from L2: a few KB next to the >= 100 KB the CTA normalises).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(512)
 gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const double* __restrict__ sums,
                 const double* __restrict__ ps1, const double* __restrict__ ps2,
@@ -151,6 +157,10 @@ gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const d
       const int gi = (c0 + i) / cpg;
       ka[i] = s_rstd[gi] * gamma[c0 + i];
       kb[i] = beta[c0 + i] - s_mean[gi] * ka[i];
+      if (silu) {
+        ka[i] *= 0.5f;
+        kb[i] *= 0.5f;
+      }
     }
     auto load4 = [&](uint4 (&u)[4], int r) {
 #pragma unroll
@@ -169,9 +179,10 @@ gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const d
         unpack8(u[b], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float y = fmaf(f[i], ka[i], kb[i]);
-          if (silu) y = __fdividef(y, 1.f + __expf(-y));
-          f[i] = y;
+          // ka / kb carry a factor 1/2 when SiLU follows: y * sigmoid(y) = h + h * tanh(h) with h = y / 2 — one MUFU
+          // operation per element instead of two (ex2 + rcp), which kept the XU pipe ~80 % busy at HBM speed
+          const float h = fmaf(f[i], ka[i], kb[i]);
+          f[i] = silu ? fmaf(h, tanh_approx(h), h) : h;
         }
         *reinterpret_cast<uint4*>(out + (base + r + b * rpi) * ldo + c0) =
             make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -389,7 +400,27 @@ extern "C" int ttvdm_groupnorm(const ttvdm_groupnorm_params* p, void* stream_) {
     gn_stats_kernel<<<grid, threads, 0, stream>>>(t1, t2, C, p->rows_per_inst, rows_per_cta, static_cast<double*>(p->stats));
     TTVDM_CHECK_LAUNCH("gn_stats_kernel");
   }
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(s1, s2, p->rows_per_inst, rows_per_cta,
+  // The apply pass is elementwise, so its chunking is free: ONE wave of CTAs (as many as fit on the SMs at once, never
+  // more), each walking a long row range — the per-CTA setup (group statistics from the producer sums, affine
+  // coefficients) is ~2-3 us and was 35-40 % of a CTA's life with the statistics pass' 4-step chunks.
+  static int n_sm = 0, occ512 = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ512, gn_apply_kernel, 512, 0) != cudaSuccess || occ512 < 1) occ512 = 1;
+  }
+  int a_rows_per_cta = rows_per_cta, a_chunks = chunks;
+  if (threads == 512) {
+    const int slots = n_sm * occ512;
+    int want = slots / n_inst;
+    if (want < 1) want = 1;
+    a_rows_per_cta = ((p->rows_per_inst + want - 1) / want + granule - 1) / granule * granule;
+    if (a_rows_per_cta < rows_per_cta) a_rows_per_cta = rows_per_cta;
+    if (a_rows_per_cta > p->rows_per_inst) a_rows_per_cta = p->rows_per_inst;
+    a_chunks = (p->rows_per_inst + a_rows_per_cta - 1) / a_rows_per_cta;
+  }
+  gn_apply_kernel<<<dim3(a_chunks, n_inst), threads, 0, stream>>>(s1, s2, p->rows_per_inst, a_rows_per_cta,
                                                 need_pass ? static_cast<const double*>(p->stats) : nullptr, ps1, ps2,
                                                 p->gamma, p->beta, p->eps, p->silu,
                                                 static_cast<__nv_bfloat16*>(p->out), p->ldo);

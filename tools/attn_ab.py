@@ -4,7 +4,7 @@ times at the three UNet levels with a 192 MB L2 flush between launches. The shar
 comes from TTVDM_ATTN_POLY (pairs of every 8, read once per process), so the driver loop at the bottom re-runs this file
 per setting.
 
-    python tools/attn_ab.py            # sweep 0 / 2 / 3 / 4 in subprocesses, writes gpurun_out/attn_ab.json
+    python tools/attn_ab.py [poly[:split[:pingpong]] ...]   # default sweep 0 / 2 / 3 / 4 in subprocesses, writes gpurun_out/attn_ab.json
 """
 import json
 import os
@@ -41,7 +41,7 @@ def child():
         torch.cuda.synchronize()
         return {"own": rel(out, ref), "torch_bf16": rel(tb, ref)}
 
-    res = {"poly_of_8": os.environ.get("TTVDM_ATTN_POLY", "default"), "acc": {}, "time": {}}
+    res = {"poly_of_8": os.environ.get("TTVDM_ATTN_POLY", "default"), "split": os.environ.get("TTVDM_ATTN_SPLIT", "default"), "pingpong": os.environ.get("TTVDM_ATTN_PINGPONG", "default"), "acc": {}, "time": {}}
     for name, (n, h, S, gain) in {"S384": (3, 5, 384, 1.0), "S200_ragged": (2, 2, 200, 1.0), "S24": (4, 20, 24, 1.0),
                                   "S1536": (2, 5, 1536, 1.0), "S1536_peaky": (2, 5, 1536, 4.0),
                                   "S2304_peaky8": (2, 10, 2304, 8.0), "S9216": (1, 5, 9216, 1.0),
@@ -80,9 +80,9 @@ if __name__ == "__main__":
     else:
         rows = []
         for thr in sys.argv[1:] or ["0", "2", "3", "4"]:
-            env = dict(os.environ, TTVDM_ATTN_POLY=thr)
+            env = dict(os.environ, TTVDM_ATTN_POLY=thr.split(":")[0], TTVDM_ATTN_SPLIT=(thr.split(":") + ["1", "0"])[1], TTVDM_ATTN_PINGPONG=(thr.split(":") + ["1", "0"])[2])
             try:
-                r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True, timeout=240)
+                r = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True, timeout=120)
                 line = [ln for ln in r.stdout.splitlines() if ln.startswith("ATTN_AB ")]
                 rows.append(json.loads(line[0][8:]) if line else {"poly_of_8": thr, "error": (r.stdout + r.stderr)[-2000:]})
             except subprocess.TimeoutExpired:

@@ -52,3 +52,8 @@ for c, tag in ev[200:1000]:
     last = (c, tag)
 print("MMA issuer phase averages:", "  ".join("%s->%s %.0f(n=%d)" % (names.get(a, hex(a)), names.get(b, hex(b)), sum(v) / len(v), len(v))
                                            for (a, b), v in sorted(seg.items())))
+# ---- relative phase of the two Q tiles: start of exp phase (tag 4) of T0 vs T1, modulo the period
+e0 = [((x >> 8) - base) for x in t[1] if x and (x & 255) == 4][20:60]
+e1 = [((x >> 8) - base) for x in t[2] if x and (x & 255) == 4][20:60]
+if e0 and e1:
+    print("exp-phase start offsets T1 - T0 (cycles):", " ".join(str(b - a) for a, b in list(zip(e0, e1))[:24]))
