@@ -99,7 +99,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 gn_apply_kernel(GnSrc s1, GnSrc s2, int rows_per_inst, int rows_per_cta, const double* __restrict__ sums,
                 const double* __restrict__ ps1, const double* __restrict__ ps2,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,

@@ -215,6 +215,8 @@ def main():
         jobs = []
     if "--attn" in sys.argv:
         jobs = jobs[17:]
+    if "--gemm-only" in sys.argv:
+        jobs = jobs[:17]
     table = []
     for j in jobs:
         try:
