@@ -13,6 +13,8 @@
 //   temporal (TemporalBasicTransformerBlock.attn2): the reference's quirk — the temporal batch row (b, s) reads
 //            context (b_global * S + s) mod n_ctx (svd/diffusion_arch/transformer_temporal.py:310-319). Here a CTA
 //            serves ONE context and gathers exactly the rows that read it (s = s0(b) + n_ctx * i), so nothing is masked.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -235,6 +237,16 @@ extern "C" int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream_) {
   if (p->n_ctx <= 0 || (!p->temporal && p->batch_offset + b_local > p->n_ctx))
     return fail(TTVDM_ERR_SHAPE, "attn_cross: batch %d+%d exceeds n_ctx=%d", p->batch_offset, b_local, p->n_ctx);
   if (p->heads <= 0 || p->heads > 65535 || p->n_ctx > 65535) return fail(TTVDM_ERR_SHAPE, "attn_cross: grid too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  {
+    // tcgen05 / TMA path (the flash kernel's cross mode) for context strides <= 2; TTVDM_XATTN_LEGACY=1 keeps the
+    // warp-level mma.sync kernel below for A/B runs, and it remains the path for n_ctx > 2 temporal calls
+    static const int legacy = getenv("TTVDM_XATTN_LEGACY") ? atoi(getenv("TTVDM_XATTN_LEGACY")) : 0;
+    if (!legacy) {
+      const int rc = launch_attn_cross_tc(p, stream);
+      if (rc >= 0) return rc;
+    }
+  }
   XaArgs g;
   g.q = static_cast<const __nv_bfloat16*>(p->q);
   g.kc = static_cast<const __nv_bfloat16*>(p->kc);
@@ -266,7 +278,6 @@ extern "C" int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream_) {
   const int pairs = (p->L + 15) / 16;
   const size_t smem = (size_t)(2 * pairs * 16 + kXaWarps * 16) * kXaRowBytes;
   dim3 grid(chunks, p->heads, p->n_ctx);
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
 #define XA_LAUNCH(P)                                                                                              \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \

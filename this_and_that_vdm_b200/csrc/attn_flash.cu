@@ -63,6 +63,12 @@ struct AttnArgs {
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* out;
   int ldo;
+  // kCross only (cross-attention against one <= 128-key context tile, include/ttvdm.h ttvdm_xattn_params): rows are
+  // addressed as (unit = (b_local, f), s); a work item takes 256 rows s = s0 + q_stride * i of one unit
+  int q_stride;      // 1 (spatial) or n_ctx (temporal: the rows of a unit that read one context)
+  int S, F;          // rows per unit in memory, frames per batch element
+  int n_units;       // b_local * F
+  int n_ctx, batch_offset, temporal;
 #ifdef TTVDM_ATTN_TRACE
   long long* trace;  // [3 classes][kTraceCap] (clock << 8 | tag) event log of one CTA (debug builds only)
 #endif
@@ -112,7 +118,12 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, fl
 // kPoly of every 8 column pairs take their exponential on the FMA pipe (exp2_poly_pair), the rest on the MUFU: the
 // softmax of two 128 x 128 tiles is 2048 MUFU cycles per KV tile on one SM (16 results per clock) against 1024 cycles of
 // tensor-pipe work, so the MUFU is what bounds the kernel at d = 64 unless part of the exponentials leaves it.
-template <int kPoly>
+// kCross: cross-attention against the short CLIP context (K6 / K8) on the same pipeline. The whole K / V of a
+// (context, head) is ONE ragged KV tile (L <= 128 keys: the masked path), the Q tiles of a work item are 2 x 128 rows of
+// one (b, f) unit fetched by a 3-D TMA box whose row dimension has element stride q_stride — for the temporal layers
+// that gathers exactly the rows s = s0 + n_ctx * i that read this context (the reference's quirk,
+// svd/diffusion_arch/transformer_temporal.py:310-319), so nothing is masked or computed twice.
+template <int kPoly, bool kCross>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
@@ -145,18 +156,39 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // set-up and exposed latency per item.
   const int total_works = g.q_tiles * g.heads * g.units;
   struct Work {
-    int q_row0, q_left, head, n_kv_tiles, kv_row_base;
+    long long q_row0;  // global query row of Q tile 0, row 0 (row i of the item is q_row0 + i * q_stride)
+    int q_left, head, n_kv_tiles, kv_row_base;
+    int unit, s_first;  // kCross: TMA coordinates of the item's first row
   };
   auto decode = [&](int w) -> Work {
     Work k;
     const int qt = w % g.q_tiles;
     const int hu = w / g.q_tiles;
     k.head = hu % g.heads;
-    const int unit = hu / g.heads;
-    k.q_row0 = unit * g.seq_q + qt * (kQT * kQTiles);  // global query row of Q tile 0, row 0
-    k.q_left = g.seq_q - qt * (kQT * kQTiles);          // valid query rows of this item (> 0)
-    k.n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
-    k.kv_row_base = unit * g.seq_kv;
+    if (!kCross) {
+      const int unit = hu / g.heads;
+      k.q_row0 = (long long)unit * g.seq_q + qt * (kQT * kQTiles);
+      k.q_left = g.seq_q - qt * (kQT * kQTiles);  // valid query rows of this item (> 0)
+      k.n_kv_tiles = (g.seq_kv + kKT - 1) / kKT;
+      k.kv_row_base = unit * g.seq_kv;
+      k.unit = unit;
+      k.s_first = 0;
+    } else {
+      // units = n_units (spatial: context = global batch index of the unit) or n_ctx * n_units (temporal)
+      const int uc = hu / g.heads;
+      const int unit = g.temporal ? uc % g.n_units : uc;
+      const int b_glob = g.batch_offset + unit / g.F;
+      const int ctx = g.temporal ? uc / g.n_units : b_glob;
+      int s0 = 0;
+      if (g.temporal) s0 = (int)((((long long)ctx - (long long)b_glob * g.S) % g.n_ctx + g.n_ctx) % g.n_ctx);
+      const int rows = (g.S - s0 + g.q_stride - 1) / g.q_stride;  // rows of this unit that read this context
+      k.unit = unit;
+      k.s_first = s0 + g.q_stride * qt * (kQT * kQTiles);
+      k.q_row0 = (long long)unit * g.S + k.s_first;
+      k.q_left = rows - qt * (kQT * kQTiles);  // may be <= 0 for the last item of a unit with s0 > 0
+      k.n_kv_tiles = 1;
+      k.kv_row_base = ctx * g.seq_kv;
+    }
     return k;
   };
 
@@ -205,8 +237,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_expect_tx(&q_full[qb], kQTiles * kTileBytes);
         // both Q tiles are always loaded: a tile past the item's rows holds the next image's rows or TMA zero fill
         // and is computed but never stored
-        for (int t = 0; t < kQTiles; ++t)
-          tma_load_2d(sQ + (qb * kQTiles + t) * kTileBytes, &tmQ, &q_full[qb], k.head * kD, k.q_row0 + t * kQT);
+        for (int t = 0; t < kQTiles; ++t) {
+          if (!kCross) tma_load_2d(sQ + (qb * kQTiles + t) * kTileBytes, &tmQ, &q_full[qb], k.head * kD, (int)k.q_row0 + t * kQT);
+          else tma_load_3d(sQ + (qb * kQTiles + t) * kTileBytes, &tmQ, &q_full[qb], k.head * kD, k.s_first + t * kQT * g.q_stride, k.unit);
+        }
         for (int j = 0; j < k.n_kv_tiles; ++j, ++kt) {
           const int st = kt % kKV;
           const uint32_t ph = (kt / kKV) & 1;
@@ -405,7 +439,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       mbar_arrive(&o_free[t]);  // O_t is in registers: the next item's first P V may overwrite it
       if (r < q_valid) {
-        __nv_bfloat16* orow = g.out + (long long)(k.q_row0 + t * kQT + r) * g.ldo + k.head * kD;
+        __nv_bfloat16* orow = g.out + (k.q_row0 + (long long)(t * kQT + r) * (kCross ? g.q_stride : 1)) * g.ldo + k.head * kD;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
@@ -426,14 +460,21 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, int ldk, const void* v, int ldv,
-                       long long kv_rows, const AttnArgs& g, int units, cudaStream_t stream) {
+                       long long kv_rows, const AttnArgs& g, int units, cudaStream_t stream, bool cross = false) {
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   const uint32_t box[2] = {kD, 128};
-  {
+  if (!cross) {
     uint64_t dims[2] = {(uint64_t)g.heads * kD, (uint64_t)q_rows};
     uint64_t str[1] = {(uint64_t)ldq * 2};
     if ((rc = make_tmap_bf16(&tmQ, q, 2, dims, str, box))) return rc;
+  } else {
+    // (channel, s, unit) with element stride q_stride along s: a box of 128 * q_stride positions delivers 128 rows
+    uint64_t dims[3] = {(uint64_t)g.heads * kD, (uint64_t)g.S, (uint64_t)g.n_units};
+    uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)g.S * ldq * 2};
+    uint32_t box3[3] = {kD, (uint32_t)(128 * g.q_stride), 1};
+    uint32_t est[3] = {1, (uint32_t)g.q_stride, 1};
+    if ((rc = make_tmap_bf16(&tmQ, q, 3, dims, str, box3, true, est))) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)g.heads * kD, (uint64_t)kv_rows};
@@ -443,14 +484,14 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     if ((rc = make_tmap_bf16(&tmV, v, 2, dims, strv, box))) return rc;
   }
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnArgs);
-  static const Kern kerns[5] = {attn_flash_kernel<0>, attn_flash_kernel<1>, attn_flash_kernel<2>, attn_flash_kernel<3>,
-                                attn_flash_kernel<4>};
+  static const Kern kerns[6] = {attn_flash_kernel<0, false>, attn_flash_kernel<1, false>, attn_flash_kernel<2, false>,
+                                attn_flash_kernel<3, false>, attn_flash_kernel<4, false>, attn_flash_kernel<0, true>};
   static int poly = -1;  // column pairs of every 8 whose exponential runs on the FMA pipe (TTVDM_ATTN_POLY: A/B runs)
   if (poly < 0) {
     const char* e = getenv("TTVDM_ATTN_POLY");
     int v = e ? atoi(e) : kAttnPolyDefault;
     if (v < 0 || v > 4) v = kAttnPolyDefault;
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 6; ++i) {
       cudaError_t ce = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
       if (ce != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     }
@@ -467,9 +508,37 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = (int)(works < n_sm ? works : n_sm);  // persistent: one CTA per SM
-  kerns[poly]<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, ga);
+  kerns[cross ? 5 : poly]<<<grid, kAttnThreads, kAttnSmem, stream>>>(tmQ, tmK, tmV, ga);
   TTVDM_CHECK_LAUNCH("attn_flash_kernel");
   return 0;
+}
+
+int launch_attn_cross_tc(const ttvdm_xattn_params* p, cudaStream_t stream) {
+  const int st = p->temporal ? p->n_ctx : 1;
+  if (st > 2 || p->L > kKT) return -1;  // a 256-position TMA box holds 128 rows only up to stride 2
+  const int b_local = p->rows / (p->F * p->S);
+  AttnArgs g{};
+  g.seq_q = 0;
+  g.seq_kv = p->L;
+  g.q_stride = st;
+  g.S = p->S;
+  g.F = p->F;
+  g.n_units = b_local * p->F;
+  g.n_ctx = p->n_ctx;
+  g.batch_offset = p->batch_offset;
+  g.temporal = p->temporal ? 1 : 0;
+  const int rows_per_unit = (p->S + st - 1) / st;
+  g.q_tiles = (rows_per_unit + kQT * kQTiles - 1) / (kQT * kQTiles);
+  g.heads = p->heads;
+  g.scale_log2 = p->scale * 1.4426950408889634f;
+  g.out = static_cast<__nv_bfloat16*>(p->out);
+  g.ldo = p->ldo;
+#ifdef TTVDM_ATTN_TRACE
+  g.trace = nullptr;
+#endif
+  const int ldkv = p->heads * kD;
+  const int units = g.temporal ? p->n_ctx * g.n_units : g.n_units;
+  return launch_attn(p->q, p->ldq, p->rows, p->kc, ldkv, p->vc, ldkv, (long long)p->n_ctx * p->L, g, units, stream, true);
 }
 
 }  // namespace ttvdm

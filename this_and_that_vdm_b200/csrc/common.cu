@@ -62,7 +62,7 @@ void reset_init() {
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128) {
+                   const uint32_t* box, bool swizzle128, const uint32_t* elem_strides) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5];
@@ -70,7 +70,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(TTVDM_ERR_SHAPE, "tensor map base not 16B aligned");

@@ -34,7 +34,9 @@ void reset_init();
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128 = true);
+                   const uint32_t* box, bool swizzle128 = true, const uint32_t* elem_strides = nullptr);
+// cross-attention through the tcgen05 flash kernel (attn_flash.cu); returns -1 if the call's shape is not covered
+int launch_attn_cross_tc(const ttvdm_xattn_params* p, cudaStream_t stream);
 
 #define TTVDM_CHECK_LAUNCH(name)                                                                  \
   do {                                                                                            \
