@@ -516,6 +516,10 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
 int launch_attn_cross_tc(const ttvdm_xattn_params* p, cudaStream_t stream) {
   const int st = p->temporal ? p->n_ctx : 1;
   if (st > 2 || p->L > kKT) return -1;  // a 256-position TMA box holds 128 rows only up to stride 2
+  // Work items are 256 rows of ONE (b, f) unit: below ~2 items per unit the padding of the last item and the per-item
+  // pipeline latency outweigh the tensor-core path (measured on B200, tools/xattn_ab.py: S = 576 temporal 0.068 vs
+  // 0.057 ms for the warp-level kernel, S = 576 spatial 0.047 vs 0.051, S >= 2304 25-30 % faster)
+  if ((p->S + st - 1) / st < 512) return -1;
   const int b_local = p->rows / (p->F * p->S);
   AttnArgs g{};
   g.seq_q = 0;
