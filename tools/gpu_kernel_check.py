@@ -413,6 +413,12 @@ CASES = [
     ("attn_cross_spatial_L17_tinyS", lambda: case_attn_cross(B=3, F=2, S=5, heads=2, L=17, n_ctx=3)),
     ("attn_cross_temporal_3ctx", lambda: case_attn_cross(B=3, F=2, S=70, heads=2, L=33, temporal=True, n_ctx=3)),
     ("attn_cross_temporal_3ctx_shard", lambda: case_attn_cross(B=1, F=3, S=49, heads=2, L=64, temporal=True, n_ctx=3, batch_offset=2)),
+    # S / n_ctx >= 512 rows per (unit, context): these take the tcgen05 / TMA cross mode of the flash kernel
+    ("attn_cross_spatial_tc", lambda: case_attn_cross(B=2, F=2, S=600, heads=5, L=78)),
+    ("attn_cross_temporal_tc", lambda: case_attn_cross(B=2, F=2, S=1100, heads=5, L=78, temporal=True)),
+    ("attn_cross_temporal_tc_oddS_shard", lambda: case_attn_cross(B=1, F=3, S=1101, heads=2, L=77, temporal=True, batch_offset=1)),
+    ("attn_cross_spatial_tc_L128_shard", lambda: case_attn_cross(B=1, F=2, S=520, heads=3, L=128, batch_offset=1)),
+    ("attn_cross_spatial_tc_L1", lambda: case_attn_cross(B=2, F=1, S=512, heads=2, L=1)),
     ("attn_temporal", lambda: case_attn_temporal()),
     ("attn_temporal_F16", lambda: case_attn_temporal(B=1, F=16, S=33, heads=2)),
     ("attn_temporal_F3_ragged", lambda: case_attn_temporal(B=2, F=3, S=7, heads=3)),
