@@ -173,7 +173,12 @@ def run_ours(args):
     from this_and_that_vdm_b200.sharding import plan, run_sharded
     K = args.videos if args.videos > 0 else world
     cond_all = synth_inputs(h, w, K, seed=0) if rank == 0 else None
-    den = FusedDenoiser(unet._get_engine(), cn._get_engine())
+    vgl = not args.vl
+    if args.vl:
+        args.no_eager = args.no_cpu_baseline = args.no_full_pipeline = True
+        if world > 1:
+            raise SystemExit("--vl is a single-GPU line")
+    den = FusedDenoiser(unet._get_engine(), cn._get_engine() if vgl else None)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     my_plan = plan(K, world)[rank]
     split_pairs = sum(1 for a in plan(K, world)[0] if a.b_local == 1) > 0 or any(
@@ -183,7 +188,8 @@ def run_ours(args):
         idx = [v, K + v]
         state = c["latents"][v].clone().contiguous()
         den.prepare(c["encoder_hidden_states"][idx], c["image_latents"][idx], c["added_time_ids"][idx], sigmas,
-                    timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][v])
+                    timesteps, guidance, num_frames=FRAMES, height=h, width=w,
+                    controlnet_cond=c["controlnet_cond"][v] if vgl else None)
         for i in range(NUM_STEPS):
             den.step(i, state)
         return state
@@ -207,7 +213,8 @@ def run_ours(args):
         c = cond_dev
         state = c["latents"][0].clone().contiguous()
         den.prepare(c["encoder_hidden_states"][[0, K]], c["image_latents"][[0, K]], c["added_time_ids"][[0, K]],
-                    sigmas, timesteps, guidance, num_frames=FRAMES, height=h, width=w, controlnet_cond=c["controlnet_cond"][0])
+                    sigmas, timesteps, guidance, num_frames=FRAMES, height=h, width=w,
+                    controlnet_cond=c["controlnet_cond"][0] if vgl else None)
         den.step(0, state)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -247,23 +254,30 @@ def run_ours(args):
     # denoises its share, ONE gather, rank 0 reads the latents back.
     n_e2e = max(5, min(args.steps, 8)) if not args.quick_e2e else 1
     if world == 1:
-        pipe = StableVideoDiffusionControlNetPipeline.from_pretrained(None, unet=unet).to(dev)
+        if vgl:
+            pipe = StableVideoDiffusionControlNetPipeline.from_pretrained(None, unet=unet).to(dev)
+        else:
+            from svd.pipeline_stable_video_diffusion import StableVideoDiffusionPipeline
+            pipe = StableVideoDiffusionPipeline.from_pretrained(None, unet=unet).to(dev)
         host = synth_inputs(h, w, 1, seed=rank)
+        if not vgl:
+            host.pop("controlnet_cond")
         host = {k: v.pin_memory() for k, v in host.items()}
         h2d = sum(v.numel() * v.element_size() for v in host.values()) * K
         out_host = torch.empty(1, FRAMES, 4, h, w, dtype=torch.float32).pin_memory()
         d2h = out_host.numel() * 4 * K
-        e2e_api = "StableVideoDiffusionControlNetPipeline.__call__ (latent mode)"
+        e2e_api = ("StableVideoDiffusionControlNetPipeline" if vgl else "StableVideoDiffusionPipeline") + ".__call__ (latent mode)"
 
         def one_round_e2e():
             for _ in range(K):
-                res = pipe(controlnet=cn, height=args.height, width=args.width, num_frames=FRAMES,
+                extra = dict(controlnet=cn, guess_mode=False,
+                             controlnet_cond_latents=host["controlnet_cond"][0].to(dev, non_blocking=True)) if vgl else {}
+                res = pipe(height=args.height, width=args.width, num_frames=FRAMES,
                            num_inference_steps=NUM_STEPS, min_guidance_scale=1.0, max_guidance_scale=3.0, fps=7,
-                           motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent", guess_mode=False,
+                           motion_bucket_id=200, noise_aug_strength=0.1, output_type="latent",
                            latents=host["latents"].to(dev, non_blocking=True) / sched.init_noise_sigma,
                            encoder_hidden_states=host["encoder_hidden_states"].to(dev, non_blocking=True),
-                           image_latents=host["image_latents"].to(dev, non_blocking=True),
-                           controlnet_cond_latents=host["controlnet_cond"][0].to(dev, non_blocking=True))
+                           image_latents=host["image_latents"].to(dev, non_blocking=True), **extra)
                 out_host.copy_(res.frames, non_blocking=True)
             torch.cuda.synchronize()
     else:
@@ -325,7 +339,7 @@ def run_ours(args):
                                              "launches": v["launches"],
                                              "tflops": round(v["flops"] / v["ms"] / 1e9, 1) if v["flops"] else None}
                   for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-        gemm_alg, attn_alg, _ = step_flops_split(h, w, 2, True)
+        gemm_alg, attn_alg, _ = step_flops_split(h, w, 2, vgl)
         g = fam.get("ttvdm_gemm", {"ms": 1.0, "launches": 1})
         achieved = gemm_alg / g["launches"] / (g["ms"] / g["launches"]) / 1e9  # TFLOP/s: alg flops per launch / avg ms
         roof = {"kernel": "gemm_kernel (linear + conv3x3 + temporal-conv family)", "bound": "tensor",
@@ -334,9 +348,9 @@ def run_ours(args):
                 "peak_source": peaks["source"],
                 "launches_per_step": g["launches"], "avg_launch_ms": round(g["ms"] / g["launches"], 4),
                 "algorithmic_tflop_per_step": round(gemm_alg / 1e12, 3),
-                "whole_step": {"algorithmic_tflop": round(step_flops(h, w, 2, True) / 1e12, 3),
-                               "achieved_tflops": round(step_flops(h, w, 2, True) * NUM_STEPS / (ms_per_video / 1e3) / 1e12, 1),
-                               "frac": round(step_flops(h, w, 2, True) * NUM_STEPS / (ms_per_video / 1e3) / 1e12 / peaks["bf16_tflops"], 4)},
+                "whole_step": {"algorithmic_tflop": round(step_flops(h, w, 2, vgl) / 1e12, 3),
+                               "achieved_tflops": round(step_flops(h, w, 2, vgl) * NUM_STEPS / (ms_per_video / 1e3) / 1e12, 1),
+                               "frac": round(step_flops(h, w, 2, vgl) * NUM_STEPS / (ms_per_video / 1e3) / 1e12 / peaks["bf16_tflops"], 4)},
                 "attention": {"algorithmic_tflop_per_step": round(attn_alg / 1e12, 3),
                               "achieved_tflops": round(attn_alg / (fam.get("ttvdm_attn_spatial", {"ms": 1})["ms"] + fam.get("ttvdm_attn_cross", {"ms": 0})["ms"]) / 1e9, 1)}}
 
@@ -359,13 +373,13 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": "frames/sec for 14-frame 576x1024 VGL, 25 Euler steps" if (args.height, args.width) == (576, 1024)
-            else f"frames/sec for 14-frame {args.height}x{args.width} VGL, 25 Euler steps",
+            "metric": "frames/sec for 14-frame 576x1024 VGL, 25 Euler steps" if (args.height, args.width) == (576, 1024) and vgl
+            else f"frames/sec for 14-frame {args.height}x{args.width} {'VGL' if vgl else 'VL'}, 25 Euler steps",
             "value": round(value, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_video, 2), "higher_is_better": True,
             "scaling": "weak" if args.videos <= 0 else "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, seeded N(0,1) latents/conditioning)",
-            "config": {"workload": f"VGL (UNet+GestureNet) 25-step Euler, 14x{args.height}x{args.width}, CFG pair (B=2) per video, "
+            "config": {"workload": f"{'VGL (UNet+GestureNet)' if vgl else 'VL (UNet only)'} 25-step Euler, 14x{args.height}x{args.width}, CFG pair (B=2) per video, "
                                    f"{K} video(s) per round on {world} GPU(s)", "videos": K,
                        "step": f"one round = {K} video(s) x 25 Euler steps", "latent": [FRAMES, 4, h, w],
                        "parallelism": f"dp{world}: " + ("split CFG pairs (uncond / cond halves on two ranks, one 2-rank exchange of "
@@ -556,6 +570,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--videos", type=int, default=0,
                     help="videos per round (BASELINE.json configs[4]); default = one per GPU (weak scaling)")
+    ap.add_argument("--vl", action="store_true",
+                    help="VL instead of VGL: UNet only through StableVideoDiffusionPipeline (BASELINE config 2); N = 1, no "
+                         "eager / CPU / full-pipeline legs")
     ap.add_argument("--height", type=int, default=576)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
