@@ -77,8 +77,8 @@ int main() {
   long long* d; cudaMalloc(&d, 128); cudaMemset(d, 0, 128);
   const char* names[6] = {"0 overwrite+commit", "1 overwrite, no commit", "2 accumulate+commit", "3 accumulate, no commit",
                           "4 two issuers (overwrite+commit)", "5 overwrite+commit, distinct A"};
-  for (int N : {64, 128, 256}) {
-    for (int mode = 0; mode < 6; ++mode) {
+  for (int N : {64, 80, 96, 128, 160, 192, 240, 256}) {
+    for (int mode = 0; mode < 6; mode += (N == 64 || N == 128 || N == 256) ? 1 : 6) {
       printf("N=%3d  %-34s cycles/group:", N, names[mode]);
       one<1>(d, mode, N); one<2>(d, mode, N); one<4>(d, mode, N); one<8>(d, mode, N); one<16>(d, mode, N);
       printf("\n");
