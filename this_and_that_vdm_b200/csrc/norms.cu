@@ -262,84 +262,110 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, i
 // group is a contiguous 128-byte line or more), 32 / kLanes rows per warp. Same arithmetic order per element as
 // layernorm_kernel up to the reduction tree.
 template <int kLanes>
-__global__ void layernorm_vec_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, const float* __restrict__ addvec,
-                                     int F, int S, __nv_bfloat16* __restrict__ sum_out, int ldsum,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                     __nv_bfloat16* __restrict__ out, int ldo) {
+__global__ void __launch_bounds__(256, 2)
+layernorm_vec_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int rows, const float* __restrict__ addvec,
+                     int F, int S, __nv_bfloat16* __restrict__ sum_out, int ldsum,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     __nv_bfloat16* __restrict__ out, int ldo) {
+  // Persistent: the grid is one wave of CTAs and every warp walks row groups gw, gw + n_warps, ... with the NEXT group's
+  // five 16-byte loads issued before the current group is reduced (round 2: 8064 one-shot CTAs per level-0 call ran at
+  // 4.3 TB/s; a warp's load -> shuffle -> load gamma/beta -> store chain was exposed once per CTA). Two CTAs per SM at
+  // 128 registers measured best (level 0: 0.0705 -> 0.0676 ms; three CTAs at 80 registers spill: 0.098 ms).
   constexpr int kC = 40 * kLanes;
   constexpr int kRowsPerWarp = 32 / kLanes;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int sub = lane % kLanes;
-  const long long row = (long long)warp * kRowsPerWarp + lane / kLanes;
-  const bool live = row < rows;  // whole lane groups are live or not; dead groups still take part in the shuffles
-  float v[5][8];
-  float s = 0.f;
-  if (live) {
-    const float* av = (addvec != nullptr) ? addvec + (size_t)((row / S) % F) * kC : nullptr;
-    uint4 raw[5];
+  const long long n_groups = ((long long)rows + kRowsPerWarp - 1) / kRowsPerWarp;
+  auto load_raw = [&](long long grp, uint4 (&r)[5]) {
+    const long long row = grp * kRowsPerWarp + lane / kLanes;
+    if (row < rows) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) raw[i] = *reinterpret_cast<const uint4*>(x + row * ldx + (sub + i * kLanes) * 8);
+      for (int i = 0; i < 5; ++i) r[i] = *reinterpret_cast<const uint4*>(x + row * ldx + (sub + i * kLanes) * 8);
+    }
+  };
+  uint4 raw[5] = {};
+  if (warp < n_groups) load_raw(warp, raw);
+  for (long long grp = warp; grp < n_groups; grp += n_warps) {
+    const long long row = grp * kRowsPerWarp + lane / kLanes;
+    const bool live = row < rows;  // whole lane groups are live or not; dead groups still take part in the shuffles
+    float v[5][8];
+    float s = 0.f;
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+      for (int i = 0; i < 5; ++i) {
+        const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack_bf16(w[k]);
-        v[i][2 * k] = f.x;
-        v[i][2 * k + 1] = f.y;
-      }
-      if (av != nullptr) {
-        const float4 e0 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8);
-        const float4 e1 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8 + 4);
-        v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
-        v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
-        if (sum_out != nullptr) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            pk[k] = pack_bf16(v[i][2 * k], v[i][2 * k + 1]);
-            const float2 f = unpack_bf16(pk[k]);  // normalise exactly what downstream residuals will read
-            v[i][2 * k] = f.x;
-            v[i][2 * k + 1] = f.y;
-          }
-          *reinterpret_cast<uint4*>(sum_out + row * ldsum + (sub + i * kLanes) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(w[k]);
+          v[i][2 * k] = f.x;
+          v[i][2 * k + 1] = f.y;
         }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += v[i][k];
     }
-  }
+    // the raw registers are free again: the next group's loads fly under this group's reductions and stores
+    if (grp + n_warps < n_groups) load_raw(grp + n_warps, raw);
+    // loop-variant zero: keeps the 80 gamma / beta values out of registers (they are L1 hits; hoisted out of the loop they
+    // cost two thirds of the occupancy)
+    const int lv0 = (int)(grp >> 62);
+    if (live) {
+      const float* av = (addvec != nullptr) ? addvec + (size_t)((row / S) % F) * kC : nullptr;
 #pragma unroll
-  for (int o = kLanes / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / kC;
-  float ss = 0.f;
-  if (live) {
+      for (int i = 0; i < 5; ++i) {
+        if (av != nullptr) {
+          const float4 e0 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8);
+          const float4 e1 = *reinterpret_cast<const float4*>(av + (sub + i * kLanes) * 8 + 4);
+          v[i][0] += e0.x; v[i][1] += e0.y; v[i][2] += e0.z; v[i][3] += e0.w;
+          v[i][4] += e1.x; v[i][5] += e1.y; v[i][6] += e1.z; v[i][7] += e1.w;
+          if (sum_out != nullptr) {
+            uint32_t pk[4];
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
+            for (int k = 0; k < 4; ++k) {
+              pk[k] = pack_bf16(v[i][2 * k], v[i][2 * k + 1]);
+              const float2 f = unpack_bf16(pk[k]);  // normalise exactly what downstream residuals will read
+              v[i][2 * k] = f.x;
+              v[i][2 * k + 1] = f.y;
+            }
+            *reinterpret_cast<uint4*>(sum_out + row * ldsum + (sub + i * kLanes) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = v[i][k] - mean;
-        ss += d * d;
+        for (int k = 0; k < 8; ++k) s += v[i][k];
       }
-  }
+    }
 #pragma unroll
-  for (int o = kLanes / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (!live) return;
-  const float rstd = rsqrtf(ss / kC + eps);
+    for (int o = kLanes / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / kC;
+    float ss = 0.f;
+    if (live) {
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int c0 = (sub + i * kLanes) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    uint32_t pk[4];
+      for (int i = 0; i < 5; ++i)
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      pk[k] = pack_bf16((v[i][2 * k] - mean) * rstd * gg[2 * k] + bb[2 * k],
-                        (v[i][2 * k + 1] - mean) * rstd * gg[2 * k + 1] + bb[2 * k + 1]);
-    *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[i][k] - mean;
+          ss += d * d;
+        }
+    }
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (live) {
+      const float rstd = rsqrtf(ss / kC + eps);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c0 = (sub + i * kLanes) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0 + lv0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4 + lv0);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + c0 + lv0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4 + lv0);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          pk[k] = pack_bf16((v[i][2 * k] - mean) * rstd * gg[2 * k] + bb[2 * k],
+                            (v[i][2 * k + 1] - mean) * rstd * gg[2 * k + 1] + bb[2 * k + 1]);
+        *reinterpret_cast<uint4*>(out + row * ldo + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
   }
 }
 
@@ -451,7 +477,21 @@ extern "C" int ttvdm_layernorm(const ttvdm_layernorm_params* p, void* stream_) {
     const int lanes = p->C / 40;
     const int rows_per_warp = 32 / lanes;
     const int warps = (p->rows + rows_per_warp - 1) / rows_per_warp;
-    const int vgrid = (warps + (threads / 32) - 1) / (threads / 32);
+    int vgrid = (warps + (threads / 32) - 1) / (threads / 32);
+    {
+      // one wave: as many CTAs as the device holds at once (every warp then loops over its row groups)
+      static int n_sm = 0, occ[3] = {0, 0, 0};
+      if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], layernorm_vec_kernel<8>, threads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], layernorm_vec_kernel<16>, threads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], layernorm_vec_kernel<32>, threads, 0);
+      }
+      const int o = occ[lanes == 8 ? 0 : (lanes == 16 ? 1 : 2)];
+      if (o > 0 && vgrid > n_sm * o) vgrid = n_sm * o;
+    }
 #define LNV_LAUNCH(L)                                                                                                \
   layernorm_vec_kernel<L><<<vgrid, threads, 0, stream>>>(x, p->ldx, p->rows, p->addvec, p->F, p->S, so, p->ldsum, p->gamma, \
                                                          p->beta, p->eps, o, p->ldo)
