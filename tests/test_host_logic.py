@@ -150,3 +150,20 @@ def test_layernorm_fold_schedule_vs_oracle(monkeypatch):
     # exactly the 7 LayerNorm launches per layer disappear; the folded engine's first forward also runs its one-time
     # positional-embedding projection (one cast per transformer + one GEMM per layer)
     assert plain_launches - folded_launches == 7 * 2 * n_tf - (n_tf + 2 * n_tf)
+
+
+def test_num_frames_above_kernel_limit_is_rejected_up_front():
+    """a 25-frame (SVD-XT) call must fail with a clear message at the boundary, not with a shape error deep
+    inside the first temporal transformer block."""
+    import pytest
+    from this_and_that_vdm_b200 import lib
+    from this_and_that_vdm_b200.engine import MAX_FRAMES
+    from this_and_that_vdm_b200.sampler import FusedDenoiser
+
+    class _E:  # enough of an engine for prepare() to reach the check
+        device = torch.device("cpu")
+
+    den = FusedDenoiser(_E(), None, use_graph=False)
+    with pytest.raises(lib.TtvdmError, match="num_frames"):
+        den.prepare(torch.zeros(2, 78, 1024), torch.zeros(2, 4, 8, 8), torch.zeros(2, 3), torch.ones(26), torch.ones(25),
+                    torch.ones(MAX_FRAMES + 9), num_frames=MAX_FRAMES + 9, height=8, width=8)

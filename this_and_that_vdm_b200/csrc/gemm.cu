@@ -1110,8 +1110,8 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   // TMA epilogue: bf16 output, no GEGLU, 16-byte aligned rows and bases (TMA global-memory constraints)
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   g.tma_epi = (want_tma && !p->out_fp32 && (!p->geglu || (p->mode == TTVDM_A_LINEAR && p->N % 16 == 0)) && p->N % 8 == 0 && p->ldo % 8 == 0 && al16(p->out) &&
-               (!p->res1 || (p->ldr1 % 8 == 0 && al16(p->res1))) && (!p->res2 || (p->res1 && p->ldr2 % 8 == 0 && al16(p->res2))))
-                  ? 1 : 0;
+               (!p->res1 || (p->ldr1 % 8 == 0 && al16(p->res1))) && (!p->res2 || (p->res1 && p->ldr2 % 8 == 0 && al16(p->res2) && p->N % 32 == 0)))
+                  ? 1 : 0;  // res2 is applied per whole 32-column chunk there: a ragged last chunk takes the direct epilogue
   {
     static const int force_direct = getenv("TTVDM_DIRECT_EPILOGUE") != nullptr;  // A/B switch for profiling only
     if (force_direct) g.tma_epi = 0;

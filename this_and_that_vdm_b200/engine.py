@@ -25,6 +25,7 @@ import torch
 from . import lib
 
 BF16 = torch.bfloat16
+MAX_FRAMES = 16  # kTaMaxF of csrc/attn_temporal.cu (one m16 MMA tile of frames per warp)
 PAD_IN = 64  # conv_in channels padded to one 64-wide K chunk
 
 
@@ -764,6 +765,9 @@ class DenoiserEngine:
         if sample.device != self.device:
             raise lib.TtvdmError(f"sample on {sample.device}, model on {self.device}")
         B, F, Cin, H, W = sample.shape
+        if F > MAX_FRAMES:
+            raise lib.TtvdmError(f"num_frames = {F}: the temporal-attention kernel holds at most {MAX_FRAMES} frames per "
+                                 f"sequence (the reference runs 14); SVD-XT's 25-frame setting is not supported")
         if H % 8 != 0 or W % 8 != 0:
             raise ValueError(f"latent height/width must be multiples of 8 (3 stride-2 levels), got {H}x{W}")
         if ehs.shape[0] != B:

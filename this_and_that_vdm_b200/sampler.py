@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 
 from . import lib
-from .engine import PAD_IN, DenoiserEngine
+from .engine import MAX_FRAMES, PAD_IN, DenoiserEngine
 
 
 class FusedDenoiser:
@@ -62,6 +62,9 @@ class FusedDenoiser:
         self.F, self.h, self.w = num_frames, height, width
         if height % 8 or width % 8:
             raise ValueError(f"latent height/width must be multiples of 8, got {height}x{width}")
+        if num_frames > MAX_FRAMES:
+            raise lib.TtvdmError(f"num_frames = {num_frames}: the temporal-attention kernel holds at most {MAX_FRAMES} "
+                                 f"frames per sequence (the reference runs 14); SVD-XT's 25-frame setting is not supported")
         self.sigmas = [float(s) for s in sigmas]
         n = len(self.sigmas) - 1
         self.n_steps = n

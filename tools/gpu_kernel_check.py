@@ -391,6 +391,8 @@ CASES = [
     ("gemm_linear_geglu_bresident", lambda: case_gemm_linear(M=128 * 117 + 5, N=2560, K=320, geglu=True)),
     ("gemm_linear_concatK", lambda: case_gemm_linear(M=300, N=640, K=1280, a2=True)),
     ("gemm_linear_raggedN", lambda: case_gemm_linear(M=130, N=200, K=64)),
+    # N % 32 != 0 with BOTH residuals (the last 32-column chunk must not lose s2 * res2)
+    ("gemm_linear_raggedN_res12", lambda: case_gemm_linear(M=300, N=200, K=128, res=True)),
     ("gemm_linear_res_partialN", lambda: case_gemm_linear(M=128 * 300 + 17, N=320, K=320, res=True)),
     ("gemm_linear_res_640", lambda: case_gemm_linear(M=128 * 150, N=640, K=640, res=True)),
     ("gemm_linear_multitile", lambda: case_gemm_linear(M=128 * 200, N=1920, K=640, bias=False)),
