@@ -92,9 +92,11 @@ class StableVideoDiffusionControlNetPipeline(SVDPipelineBase):
             else:
                 batch_size = image.shape[0]
             ehs = self.encode_clip(image, prompt, use_text, text_encoder, device, num_videos_per_prompt, do_cfg)
-            image_t = self._preprocess_image(image, height, width).to(device)
+            # the reference draws the augmentation noise where the preprocessed image lives (the host for PIL / CPU
+            # tensors) and only then moves it: same RNG stream as the reference under torch.manual_seed / a CPU generator
+            image_t = self._preprocess_image(image, height, width)
             noise = randn_tensor(image_t.shape, generator=generator, device=image_t.device, dtype=image_t.dtype)
-            image_t = image_t + noise_aug_strength * noise
+            image_t = (image_t + noise_aug_strength * noise).to(device)
             needs_upcasting = (self.vae.dtype == torch.float16 and self.vae.config.force_upcast
                                and not getattr(self.vae, "_ttvdm_native", False))
             if needs_upcasting:
