@@ -133,8 +133,11 @@ typedef struct {
 int ttvdm_attn_spatial(const ttvdm_attn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K6/K8 — cross-attention against a short, precomputed context (L <= 128 keys); warp-level mma.sync kernel with
- * K/V of one (context, head) pinned in shared memory. q, kc, vc, out must be 16-byte aligned.
+ * K6/K8 — cross-attention against a short, precomputed context (L <= 128 keys). Units with >= 512 rows per
+ * context (and context stride <= 2) run the tcgen05 flash kernel in cross mode: the context is one ragged KV tile,
+ * the rows that read it are gathered by a 3-D TMA box with an element stride (csrc/attn_flash.cu); smaller units and
+ * n_ctx > 2 run a warp-level mma.sync kernel with K/V of one (context, head) pinned in shared memory
+ * (csrc/attn_cross.cu). q, kc, vc, out must be 16-byte aligned.
  * q: [rows, heads*64] (row stride ldq). kc/vc: [n_ctx, L, heads*64] bf16 — K/V of the constant context,
  * projected ONCE per video (reference recomputes them per frame and per pixel,
  * svd/unet_spatio_temporal_condition.py:452, svd/diffusion_arch/transformer_temporal.py:316-319).
