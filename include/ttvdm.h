@@ -156,6 +156,7 @@ typedef struct {
   int temporal;      /* 0: ctx = b_global ; 1: ctx = (b_global*S + s) mod n_ctx */
   int batch_offset;  /* global index of the first local batch element (batch sharding) */
   float scale;
+  int head_dim;      /* ABI 4: 0 or 64 (default), or 128 (warp-level kernel only; the reference UNet's class-default heads) */
 } ttvdm_xattn_params;
 int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream);
 
@@ -169,6 +170,7 @@ typedef struct {
   int ldq, ldk, ldv, ldo;
   int B, F, S, heads;
   float scale;
+  int head_dim;      /* ABI 4: 0 or 64 (default), or 128 */
 } ttvdm_tattn_params;
 int ttvdm_attn_temporal(const ttvdm_tattn_params* p, void* stream);
 

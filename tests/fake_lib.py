@@ -134,11 +134,11 @@ def attn_spatial(q, k, v, out, *, ldq, ldk, ldv, ldo, n_img, heads, seq, scale) 
     _count()
 
 
-def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale) -> None:
-    C = heads * 64
-    qq = _heads(q, rows, heads, ldq)
-    kk = _mat(kc, n_ctx * L, C, C).float().view(n_ctx, L, heads, 64)
-    vv = _mat(vc, n_ctx * L, C, C).float().view(n_ctx, L, heads, 64)
+def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale, head_dim=64) -> None:
+    C = heads * head_dim
+    qq = _heads(q, rows, heads, ldq, head_dim)
+    kk = _mat(kc, n_ctx * L, C, C).float().view(n_ctx, L, heads, head_dim)
+    vv = _mat(vc, n_ctx * L, C, C).float().view(n_ctx, L, heads, head_dim)
     r = torch.arange(rows)
     b = r // (F * S) + batch_offset
     ctx = ((b * S + r % S) % n_ctx) if temporal else b
@@ -149,13 +149,13 @@ def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, tempora
     _count()
 
 
-def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) -> None:
+def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale, head_dim=64) -> None:
     rows = B * F * S
-    qq, kk, vv = (_heads(t, rows, heads, ld).view(B, F, S, heads, 64).permute(0, 2, 3, 1, 4)
-                  for t, ld in ((q, ldq), (k, ldk), (v, ldv)))  # [B, S, heads, F, 64]
+    qq, kk, vv = (_heads(t, rows, heads, ld, head_dim).view(B, F, S, heads, head_dim).permute(0, 2, 3, 1, 4)
+                  for t, ld in ((q, ldq), (k, ldk), (v, ldv)))  # [B, S, heads, F, d]
     p = torch.softmax(qq @ kk.transpose(-1, -2) * scale, -1)
-    o = (p @ vv).permute(0, 3, 1, 2, 4).reshape(rows, heads * 64)
-    _mat(out, rows, heads * 64, ldo).copy_(o.to(BF16))
+    o = (p @ vv).permute(0, 3, 1, 2, 4).reshape(rows, heads * head_dim)
+    _mat(out, rows, heads * head_dim, ldo).copy_(o.to(BF16))
     _count()
 
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for name in declared:
         assert hasattr(l, name), name
-    assert l.ttvdm_abi_version() == 3
+    assert l.ttvdm_abi_version() == 4
     assert lib.launch_count() == 0 or lib.launch_count() > 0
 
 

@@ -167,3 +167,23 @@ def test_num_frames_above_kernel_limit_is_rejected_up_front():
     with pytest.raises(lib.TtvdmError, match="num_frames"):
         den.prepare(torch.zeros(2, 78, 1024), torch.zeros(2, 4, 8, 8), torch.zeros(2, 3), torch.ones(26), torch.ones(25),
                     torch.ones(MAX_FRAMES + 9), num_frames=MAX_FRAMES + 9, height=8, width=8)
+
+
+def test_head_dim_128_compatibility_path_vs_oracle():
+    """The reference UNet's class-default heads (5, 10, 10, 20) give head_dim 128 at level 2
+    (svd/unet_spatio_temporal_condition.py:99). Tiny analogue: 256 channels / 2 heads at level 2. The engine takes the
+    GEMM + row-softmax path for the spatial self-attention and the head_dim-128 variants of the warp-level cross /
+    temporal attention kernels; compared with the oracle (which is pinned to the reference for this head variant,
+    tests/test_reference_pin.py)."""
+    kind = dict(TINY, num_attention_heads=(1, 2, 2, 4))
+    unet, cn = build_models(kind)
+    sample, ehs, ati, cond = make_inputs(2, 4, 8, 8)
+    with torch.no_grad(), fake_lib.installed():
+        eu, ec = DenoiserEngine(unet, "unet"), DenoiserEngine(cn, "controlnet")
+        assert [t.hd for blk in eu.down for t in blk["tf"]] == [64, 64, 64, 64, 128, 128]
+        d, m = ec.controlnet_forward(sample, T0, ehs, ati, torch.cat([cond[:4], cond[:4]]), 1.0)
+        y = eu.unet_forward(sample, T0, ehs, ati, d, m)
+        cfg = oracle_cfg(kind)
+        d_ref, m_ref = O.controlnet_forward(state(cn), cfg, sample, T0, ehs, ati, torch.cat([cond[:4], cond[:4]]), 1.0)
+        y_ref = O.unet_forward(state(unet), cfg, sample, T0, ehs, ati, d_ref, m_ref)
+    assert rel_l2(m, m_ref) < CAP and rel_l2(y, y_ref) < CAP, (rel_l2(m, m_ref), rel_l2(y, y_ref))

@@ -295,6 +295,37 @@ def test_svd_b2_unet_gesturenet_vs_reference_own_forward(svd_refpin):
 
 
 @pytest.mark.slow
+def test_class_default_heads_head_dim_128_vs_reference_own_forward():
+    """The reference UNet's class-default heads (5, 10, 10, 20) (svd/unet_spatio_temporal_condition.py:99): head_dim 128 at
+    level 2. SVD widths, B = 2, 4 x 8 x 8: the engine (GEMM + row-softmax self-attention, head_dim-128 variants of the
+    warp-level cross / temporal attention kernels) against the outputs of the REFERENCE'S OWN forward
+    (tests/golden/reference_pin.pt, case svd_hd128)."""
+    from svd.temporal_controlnet import ControlNetModel
+    from svd.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel
+    from tests import refpin
+    kind, B, F, h, w = refpin.CASES["svd_hd128"]
+    unet = UNetSpatioTemporalConditionModel(num_frames=F, **kind).eval()
+    cn = ControlNetModel(**kind).eval()
+    unet.load_state_dict(refpin.fill_state_dict(((k, v.shape) for k, v in unet.state_dict().items()), seed=11))
+    cn.load_state_dict(refpin.fill_state_dict(((k, v.shape) for k, v in cn.state_dict().items()), seed=12))
+    unet, cn = unet.to("cuda"), cn.to("cuda")
+    gold = torch.load(GOLD / "reference_pin.pt", weights_only=False)["svd_hd128"]
+    sample, ehs, ati, cond = refpin.make_inputs(B, F, h, w)
+    cc = torch.cat([cond] * B)
+    t = torch.tensor(refpin.TIMESTEP)
+    with torch.no_grad():
+        y = unet(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda()).sample
+        d, m = cn(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda(), controlnet_cond=cc.cuda(), conditioning_scale=0.75,
+                  return_dict=False)
+        yg = unet(sample.cuda(), t.cuda(), ehs.cuda(), ati.cuda(), down_block_additional_residuals=d,
+                  mid_block_additional_residual=m).sample
+    errs = {"unet": rel_l2(y, gold["unet"]), "cn_mid": rel_l2(m, gold["cn_mid"]), "vgl": rel_l2(yg, gold["vgl"])}
+    print("svd head_dim 128 vs reference forward:", errs)
+    _record("svd_class_default_heads_hd128_4x8x8_vs_reference_own_forward", errs)
+    assert all(v < SVD_FWD_CAP for v in errs.values()), errs
+
+
+@pytest.mark.slow
 def test_svd_b2_fused_step_32x48_vs_oracle(svd_refpin):
     """BASELINE configs[0] size (14 x 32 x 48 latent) with B = 2: UNet + GestureNet through the fused sampler path
     (zero-conv accumulation into the skips, epilogue-fused norms) against the fp32 oracle computed here."""

@@ -21,7 +21,7 @@
 namespace ttvdm {
 
 constexpr int kXaWarps = 8;
-constexpr int kXaRowBytes = 144;  // 128 B of data + 16 B pad: conflict-free ldmatrix
+// rows of kD * 2 B of data + 16 B pad (conflict-free ldmatrix); kD = 64, or 128 for the reference UNet's class-default heads
 constexpr int kXaMaxL = 128;
 
 __device__ __forceinline__ void xa_cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -56,9 +56,11 @@ struct XaArgs {
 };
 
 // kPairs = ceil(L / 16): 16-key steps (pairs of 8-key n-tiles) that hold a valid key
-template <int kPairs>
+template <int kPairs, int kD = 64>
 __global__ void __launch_bounds__(kXaWarps * 32)
 attn_cross_kernel(const XaArgs g) {
+  constexpr int kXaRowBytes = kD * 2 + 16;
+  constexpr int kCh = kD / 8;  // 16-byte chunks per row
   extern __shared__ __align__(16) uint8_t xa_smem[];
   uint8_t* sK = xa_smem;                               // [kPairs * 16][144 B]
   uint8_t* sV = sK + kPairs * 16 * kXaRowBytes;
@@ -82,12 +84,12 @@ attn_cross_kernel(const XaArgs g) {
 
   // ---- K, V of (ctx, head) -> shared memory, rows >= L zero-filled (P is 0 there, but 0 * garbage must stay 0)
   {
-    const __nv_bfloat16* kb = g.kc + ((size_t)ctx * g.L) * (g.heads * 64) + head * 64;
-    const __nv_bfloat16* vb = g.vc + ((size_t)ctx * g.L) * (g.heads * 64) + head * 64;
-    for (int i = threadIdx.x; i < kPairs * 16 * 8; i += kXaWarps * 32) {
-      const int row = i >> 3, ch = i & 7;
+    const __nv_bfloat16* kb = g.kc + ((size_t)ctx * g.L) * (g.heads * kD) + head * kD;
+    const __nv_bfloat16* vb = g.vc + ((size_t)ctx * g.L) * (g.heads * kD) + head * kD;
+    for (int i = threadIdx.x; i < kPairs * 16 * kCh; i += kXaWarps * 32) {
+      const int row = i / kCh, ch = i % kCh;
       const int ok = row < g.L ? 16 : 0;
-      const size_t off = (size_t)(row < g.L ? row : 0) * (g.heads * 64) + ch * 8;
+      const size_t off = (size_t)(row < g.L ? row : 0) * (g.heads * kD) + ch * 8;
       xa_cp_async16(smem_u32(sK) + row * kXaRowBytes + ch * 16, kb + off, ok);
       xa_cp_async16(smem_u32(sV) + row * kXaRowBytes + ch * 16, vb + off, ok);
     }
@@ -111,13 +113,17 @@ attn_cross_kernel(const XaArgs g) {
     const long long unit_row0 = (long long)unit * g.S;
     // tile row i <-> s = s0 + stride * (16 * tt + i); rows with s >= S do not exist
     {
-      const int fr = lane >> 3, ch = lane & 7;
+      const int fr = lane >> 3;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 4 + fr;
         const int s = s0 + stride * (16 * tt + r);
         const int ok = s < g.S ? 16 : 0;
-        xa_cp_async16(sq + r * kXaRowBytes + ch * 16, g.q + (unit_row0 + (s < g.S ? s : 0)) * g.ldq + head * 64 + ch * 8, ok);
+#pragma unroll
+        for (int c8 = 0; c8 < kCh; c8 += 8) {
+          const int ch = c8 + (lane & 7);
+          xa_cp_async16(sq + r * kXaRowBytes + ch * 16, g.q + (unit_row0 + (s < g.S ? s : 0)) * g.ldq + head * kD + ch * 8, ok);
+        }
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
       __syncwarp();
@@ -129,7 +135,7 @@ attn_cross_kernel(const XaArgs g) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) sc[n][e] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < kD / 16; ++kk) {
       uint32_t a[4];
       xa_ldsm_x4(sq + (lane & 15) * kXaRowBytes + kk * 32 + (lane >> 4) * 16, a);
 #pragma unroll
@@ -172,9 +178,9 @@ attn_cross_kernel(const XaArgs g) {
     }
     const float inv[2] = {1.f / sum[0], 1.f / sum[1]};
     // ---- O = P V (16 x 64): P (bf16, unnormalised — values in (0, 1]) straight from the accumulator layout
-    float o[8][4];
+    float o[kD / 8][4];
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt)
+    for (int dt = 0; dt < kD / 8; ++dt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
 #pragma unroll
@@ -185,7 +191,7 @@ attn_cross_kernel(const XaArgs g) {
       pa[2] = pack_bf16(sc[2 * kp + 1][0], sc[2 * kp + 1][1]);
       pa[3] = pack_bf16(sc[2 * kp + 1][2], sc[2 * kp + 1][3]);
 #pragma unroll
-      for (int d2 = 0; d2 < 4; ++d2) {
+      for (int d2 = 0; d2 < kD / 16; ++d2) {
         uint32_t bm[4];
         xa_ldsm_x4_trans(sv + (kp * 16 + (lane & 15)) * kXaRowBytes + (d2 * 2 + (lane >> 4)) * 16, bm);
         xa_mma(o[d2 * 2], pa, bm[0], bm[1]);
@@ -197,21 +203,25 @@ attn_cross_kernel(const XaArgs g) {
     {
       const int r0 = lane >> 2, c0 = (lane & 3) * 2;
 #pragma unroll
-      for (int dt = 0; dt < 8; ++dt) {
+      for (int dt = 0; dt < kD / 8; ++dt) {
         *reinterpret_cast<uint32_t*>(sq_gen + r0 * kXaRowBytes + (dt * 8 + c0) * 2) =
             pack_bf16(o[dt][0] * inv[0], o[dt][1] * inv[0]);
         *reinterpret_cast<uint32_t*>(sq_gen + (r0 + 8) * kXaRowBytes + (dt * 8 + c0) * 2) =
             pack_bf16(o[dt][2] * inv[1], o[dt][3] * inv[1]);
       }
       __syncwarp();
-      const int fr = lane >> 3, ch = lane & 7;
+      const int fr = lane >> 3;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = i * 4 + fr;
         const int s = s0 + stride * (16 * tt + r);
         if (s < g.S) {
-          const uint4 u = *reinterpret_cast<const uint4*>(sq_gen + r * kXaRowBytes + ch * 16);
-          *reinterpret_cast<uint4*>(g.out + (unit_row0 + s) * g.ldo + head * 64 + ch * 8) = u;
+#pragma unroll
+          for (int c8 = 0; c8 < kCh; c8 += 8) {
+            const int ch = c8 + (lane & 7);
+            const uint4 u = *reinterpret_cast<const uint4*>(sq_gen + r * kXaRowBytes + ch * 16);
+            *reinterpret_cast<uint4*>(g.out + (unit_row0 + s) * g.ldo + head * kD + ch * 8) = u;
+          }
         }
       }
       __syncwarp();  // the tile is re-filled by the next item's cp.async
@@ -242,7 +252,7 @@ extern "C" int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream_) {
     // tcgen05 / TMA path (the flash kernel's cross mode) for context strides <= 2; TTVDM_XATTN_LEGACY=1 keeps the
     // warp-level mma.sync kernel below for A/B runs, and it remains the path for n_ctx > 2 temporal calls
     static const int legacy = getenv("TTVDM_XATTN_LEGACY") ? atoi(getenv("TTVDM_XATTN_LEGACY")) : 0;
-    if (!legacy) {
+    if (!legacy && (p->head_dim == 0 || p->head_dim == 64)) {
       const int rc = launch_attn_cross_tc(p, stream);
       if (rc >= 0) return rc;
     }
@@ -276,18 +286,23 @@ extern "C" int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream_) {
   if (chunks < 1) chunks = 1;
   g.chunks = chunks;
   const int pairs = (p->L + 15) / 16;
-  const size_t smem = (size_t)(2 * pairs * 16 + kXaWarps * 16) * kXaRowBytes;
+  const int hd = p->head_dim == 0 ? 64 : p->head_dim;
+  if (hd != 64 && hd != 128) return fail(TTVDM_ERR_SHAPE, "attn_cross: head_dim %d (64 or 128)", hd);
+  const size_t smem = (size_t)(2 * pairs * 16 + kXaWarps * 16) * (hd * 2 + 16);
   dim3 grid(chunks, p->heads, p->n_ctx);
 #define XA_LAUNCH(P)                                                                                              \
   do {                                                                                                            \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
-      cudaError_t e = cudaFuncSetAttribute(attn_cross_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                           (2 * P * 16 + kXaWarps * 16) * kXaRowBytes);                          \
+    static bool attr_set[2] = {false, false};                                                                     \
+    if (!attr_set[hd == 128]) {                                                                                   \
+      cudaError_t e = hd == 64 ? cudaFuncSetAttribute(attn_cross_kernel<P, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                                      (2 * P * 16 + kXaWarps * 16) * 144)                         \
+                               : cudaFuncSetAttribute(attn_cross_kernel<P, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                      (2 * P * 16 + kXaWarps * 16) * 272);                        \
       if (e != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn_cross: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
-      attr_set = true;                                                                                            \
+      attr_set[hd == 128] = true;                                                                                 \
     }                                                                                                             \
-    attn_cross_kernel<P><<<grid, kXaWarps * 32, smem, stream>>>(g);                                              \
+    if (hd == 64) attn_cross_kernel<P, 64><<<grid, kXaWarps * 32, smem, stream>>>(g);                             \
+    else attn_cross_kernel<P, 128><<<grid, kXaWarps * 32, smem, stream>>>(g);                                     \
   } while (0)
   switch (pairs) {
     case 1: XA_LAUNCH(1); break;

@@ -12,9 +12,9 @@
 
 namespace ttvdm {
 
-constexpr int kTaWarps = 4;        // items per CTA (one per warp)
 constexpr int kTaMaxF = 16;
-constexpr int kTaRowBytes = 144;   // 128 B of data + 16 B pad: conflict-free ldmatrix
+// head dim kD = 64 / 128: rows of kD * 2 B of data + 16 B pad (conflict-free ldmatrix); 4 / 2 items (warps) per CTA so the
+// static shared memory stays under 48 KB
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -36,10 +36,14 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(kTaWarps * 32)
+template <int kD>
+__global__ void __launch_bounds__((kD == 64 ? 4 : 2) * 32)
 attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                      const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out, int ldq, int ldk, int ldv,
                      int ldo, int B, int F, int S, int heads, float scale) {
+  constexpr int kTaWarps = kD == 64 ? 4 : 2;
+  constexpr int kTaRowBytes = kD * 2 + 16;
+  constexpr int kCh = kD / 8;  // 16-byte chunks per row
   __shared__ __align__(16) uint8_t tiles[kTaWarps][3][kTaMaxF * kTaRowBytes];  // per warp: Q (later O), K, V
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -55,16 +59,20 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
 
   // ---- Q, K, V -> shared memory: 4 frames x 8 chunks of 16 B per instruction, frames >= F zero-filled
   {
-    const int fr = lane >> 3, ch = lane & 7;
+    const int fr = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int f = i * 4 + fr;
       const int ok = f < F ? 16 : 0;
       const long long row = row0 + (long long)(f < F ? f : 0) * S;
-      const uint32_t off = f * kTaRowBytes + ch * 16;
-      cp_async16(sq + off, q + row * ldq + head * 64 + ch * 8, ok);
-      cp_async16(sk + off, k + row * ldk + head * 64 + ch * 8, ok);
-      cp_async16(sv + off, v + row * ldv + head * 64 + ch * 8, ok);
+#pragma unroll
+      for (int c8 = 0; c8 < kCh; c8 += 8) {
+        const int ch = c8 + (lane & 7);
+        const uint32_t off = f * kTaRowBytes + ch * 16;
+        cp_async16(sq + off, q + row * ldq + head * kD + ch * 8, ok);
+        cp_async16(sk + off, k + row * ldk + head * kD + ch * 8, ok);
+        cp_async16(sv + off, v + row * ldv + head * kD + ch * 8, ok);
+      }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -73,7 +81,7 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   // ---- S = Q K^T (16 x 16, fp32): 4 k-steps of 16 head-dim columns, 2 n-tiles of 8 key frames
   float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = 0; kk < kD / 16; ++kk) {
     uint32_t a[4], bm[4];
     // A: matrices (rows 0-7 | 8-15) x (cols kk*16 .. +7 | +8 .. +15)
     ldsm_x4(sq + (lane & 15) * kTaRowBytes + kk * 32 + (lane >> 4) * 16, a);
@@ -120,13 +128,13 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   pa[3] = pack_bf16(sc[1][2] * inv[1], sc[1][3] * inv[1]);
 
   // ---- O = P V (16 x 64): 8 n-tiles of 8 head-dim columns, k = 16 key frames; V^T fragments via ldmatrix.trans
-  float o[8][4];
+  float o[kD / 8][4];
 #pragma unroll
-  for (int dt = 0; dt < 8; ++dt)
+  for (int dt = 0; dt < kD / 8; ++dt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
 #pragma unroll
-  for (int d2 = 0; d2 < 4; ++d2) {
+  for (int d2 = 0; d2 < kD / 16; ++d2) {
     uint32_t bm[4];
     // matrices: (key frames 0-7 | 8-15) x head-dim tile 2*d2, then the same for tile 2*d2 + 1
     ldsm_x4_trans(sv + (lane & 15) * kTaRowBytes + (d2 * 2 + (lane >> 4)) * 16, bm);
@@ -139,18 +147,22 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
     uint8_t* so = tiles[warp][0];
     const int r0 = lane >> 2, c0 = (lane & 3) * 2;
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
+    for (int dt = 0; dt < kD / 8; ++dt) {
       *reinterpret_cast<uint32_t*>(so + r0 * kTaRowBytes + (dt * 8 + c0) * 2) = pack_bf16(o[dt][0], o[dt][1]);
       *reinterpret_cast<uint32_t*>(so + (r0 + 8) * kTaRowBytes + (dt * 8 + c0) * 2) = pack_bf16(o[dt][2], o[dt][3]);
     }
     __syncwarp();
-    const int fr = lane >> 3, ch = lane & 7;
+    const int fr = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int f = i * 4 + fr;
       if (f < F) {
-        const uint4 u = *reinterpret_cast<const uint4*>(so + f * kTaRowBytes + ch * 16);
-        *reinterpret_cast<uint4*>(out + (row0 + (long long)f * S) * ldo + head * 64 + ch * 8) = u;
+#pragma unroll
+        for (int c8 = 0; c8 < kCh; c8 += 8) {
+          const int ch = c8 + (lane & 7);
+          const uint4 u = *reinterpret_cast<const uint4*>(so + f * kTaRowBytes + ch * 16);
+          *reinterpret_cast<uint4*>(out + (row0 + (long long)f * S) * ldo + head * kD + ch * 8) = u;
+        }
       }
     }
   }
@@ -170,12 +182,22 @@ extern "C" int ttvdm_attn_temporal(const ttvdm_tattn_params* p, void* stream_) {
     return fail(TTVDM_ERR_SHAPE, "attn_temporal: q/k/v/out must be 16-byte aligned");
   const long long items = (long long)p->B * p->S * p->heads;
   if (items <= 0) return fail(TTVDM_ERR_SHAPE, "attn_temporal: empty");
-  const long long grid = (items + kTaWarps - 1) / kTaWarps;
+  const int hd = p->head_dim == 0 ? 64 : p->head_dim;
+  if (hd != 64 && hd != 128) return fail(TTVDM_ERR_SHAPE, "attn_temporal: head_dim %d (64 or 128)", hd);
+  const int warps = hd == 64 ? 4 : 2;
+  const long long grid = (items + warps - 1) / warps;
   if (grid > 0x7fffffffLL) return fail(TTVDM_ERR_SHAPE, "attn_temporal: too many items");
-  attn_temporal_kernel<<<(int)grid, kTaWarps * 32, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(p->q), static_cast<const __nv_bfloat16*>(p->k),
-      static_cast<const __nv_bfloat16*>(p->v), static_cast<__nv_bfloat16*>(p->out), p->ldq, p->ldk, p->ldv, p->ldo,
-      p->B, p->F, p->S, p->heads, p->scale);
+  auto* kq = static_cast<const __nv_bfloat16*>(p->q);
+  auto* kk = static_cast<const __nv_bfloat16*>(p->k);
+  auto* kv = static_cast<const __nv_bfloat16*>(p->v);
+  auto* ko = static_cast<__nv_bfloat16*>(p->out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (hd == 64)
+    attn_temporal_kernel<64><<<(int)grid, warps * 32, 0, st>>>(kq, kk, kv, ko, p->ldq, p->ldk, p->ldv, p->ldo, p->B, p->F,
+                                                               p->S, p->heads, p->scale);
+  else
+    attn_temporal_kernel<128><<<(int)grid, warps * 32, 0, st>>>(kq, kk, kv, ko, p->ldq, p->ldk, p->ldv, p->ldo, p->B, p->F,
+                                                                p->S, p->heads, p->scale);
   TTVDM_CHECK_LAUNCH("attn_temporal_kernel");
   return 0;
 }

@@ -109,7 +109,7 @@ int ttvdm_destroy(void) {
   return 0;
 }
 
-int ttvdm_abi_version(void) { return 3; }
+int ttvdm_abi_version(void) { return 4; }
 
 uint64_t ttvdm_launch_count(void) { return ttvdm::g_launches.load(); }
 }

@@ -139,6 +139,11 @@ class TfLayer:
 class TfW:
     C: int
     heads: int
+
+    @property
+    def hd(self) -> int:  # head dim: 64 for every shipped config, 128 at level 2 of the reference's class-default heads
+        return self.C // self.heads
+
     gn_g: torch.Tensor = None
     gn_b: torch.Tensor = None
     w_in: torch.Tensor = None
@@ -192,9 +197,10 @@ class DenoiserEngine:
         self.heads = tuple(cfg.num_attention_heads) if not isinstance(cfg.num_attention_heads, int) else \
             (cfg.num_attention_heads,) * len(self.chans)
         for c, h in zip(self.chans, self.heads):
-            if c % 64 != 0 or c // h != 64:
+            if c % 64 != 0 or c % h != 0 or c // h not in (64, 128):
                 raise lib.TtvdmError(
-                    f"sm_100a engine supports head_dim 64 and channels %% 64 == 0 (got C={c}, heads={h})")
+                    f"sm_100a engine supports head_dim 64 (and 128 on the compatibility path) with channels %% 64 == 0 "
+                    f"(got C={c}, heads={h})")
         self.temb_dim = self.chans[0] * 4
         self.add_dim = cfg.addition_time_embed_dim
         self._pos_cache: Dict[int, bool] = {}
@@ -578,14 +584,42 @@ class DenoiserEngine:
         return self._tconv(y, r.tw2, r.tb2, B=B, F=F, S=S, C=r.cout, out=out, s0=1.0 - r.alpha, res1=hs, s1=1.0,
                            res2=out_res2, s2=out_s2, gn_rpi=S)
 
+    def _self_attn_hd128(self, y, wqkv, *, n_img, S, C, heads, scale):
+        """Spatial self-attention for head_dim 128 (level 2 of the reference UNet's CLASS-DEFAULT heads (5, 10, 10, 20),
+        svd/unet_spatio_temporal_condition.py:99 — no shipped config uses it): compatibility path out of the GEMM and
+        row-softmax kernels, one (image, head) at a time — Q K^T (fp32 scores) -> softmax -> P V with V^T produced by a
+        swapped-operand GEMM per image. Correct, all sm_100a kernels, not tuned (the flash kernel's TMEM plan is d = 64)."""
+        d = 128
+        rows = n_img * S
+        Sp = (S + 63) // 64 * 64
+        wq, wk, wv = wqkv[:C], wqkv[C:2 * C], wqkv[2 * C:]
+        q = self._linear(y, wq, M=rows)
+        kh = self._empty(heads, rows, d)
+        for h in range(heads):  # K per head, contiguous [rows, 128]: the W operand of the score GEMM
+            lib.gemm(y, wk[h * d:(h + 1) * d], kh[h], M=rows, N=d, k1=C)
+        vt = torch.zeros(C, Sp, dtype=BF16, device=self.device)  # columns >= S stay zero (K padding of P V)
+        scores = self._empty(S, S, dtype=torch.float32)
+        probs = self._empty(S, Sp)
+        o = self._empty(rows, C)
+        for n in range(n_img):
+            yn = y[n * S:(n + 1) * S]
+            lib.gemm(wv, yn, vt, M=C, N=S, k1=C, ldo=Sp)  # V^T of all heads of this image: [C, Sp]
+            for h in range(heads):
+                lib.gemm(q[n * S:, h * d:], kh[h][n * S:(n + 1) * S], scores, M=S, N=S, k1=d, lda=C, s0=scale,
+                         out_fp32=True)
+                lib.softmax_rows(scores, probs, rows=S, cols=S, ldx=S, ldo=Sp, cols_out=Sp)
+                lib.gemm(probs, vt[h * d:(h + 1) * d], o[n * S:, h * d:], M=S, N=d, k1=Sp, ldo=C)
+        return o
+
     def _transformer(self, t: TfW, x, kv, *, B, F, H, W, n_ctx, batch_offset):
         """TransformerSpatioTemporalModel.forward (svd/diffusion_arch/transformer_temporal.py:276-381)."""
-        if self.fuse_layernorm:
+        if self.fuse_layernorm and t.hd == 64:
             return self._transformer_ln_folded(t, x, kv, B=B, F=F, H=H, W=W, n_ctx=n_ctx, batch_offset=batch_offset)
         S = H * W
         rows = B * F * S
         C = t.C
-        scale = 0.125
+        scale = float(t.hd) ** -0.5
+        hd = t.hd
         y = self._gn(x, t.gn_g, t.gn_b, rows=rows, rows_per_inst=S, eps=1e-6, silu=False)
         h = self._linear(y, t.w_in, M=rows, bias=t.b_in)
         qkv = q = gg = hm = None
@@ -593,15 +627,18 @@ class DenoiserEngine:
             L = ks.shape[0] // n_ctx
             # ---- spatial BasicTransformerBlock
             y = self._ln(h, ly.s_attn1.ln, rows=rows, C=C, out=y)
-            qkv = self._linear(y, ly.s_attn1.wqkv, M=rows, out=qkv)
-            o = y  # reuse
-            lib.attn_spatial(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, n_img=B * F,
-                             heads=t.heads, seq=S, scale=scale)
+            if hd == 64:
+                qkv = self._linear(y, ly.s_attn1.wqkv, M=rows, out=qkv)
+                o = y  # reuse
+                lib.attn_spatial(qkv, qkv[:, C:], qkv[:, 2 * C:], o, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, n_img=B * F,
+                                 heads=t.heads, seq=S, scale=scale)
+            else:
+                o = self._self_attn_hd128(y, ly.s_attn1.wqkv, n_img=B * F, S=S, C=C, heads=t.heads, scale=scale)
             self._linear(o, ly.s_attn1.wo, M=rows, bias=ly.s_attn1.bo, res1=h, out=h)
             y = self._ln(h, ly.s_attn2.ln, rows=rows, C=C, out=y)
             q = self._linear(y, ly.s_attn2.wq, M=rows, out=q)
             lib.attn_cross(q, ks, vs, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
-                           temporal=False, batch_offset=batch_offset, scale=scale)
+                           temporal=False, batch_offset=batch_offset, scale=scale, head_dim=hd)
             self._linear(y, ly.s_attn2.wo, M=rows, bias=ly.s_attn2.bo, res1=h, out=h)
             y = self._ln(h, ly.s_ff.ln, rows=rows, C=C, out=y)
             gg = self._linear(y, ly.s_ff.w1, M=rows, bias=ly.s_ff.b1, geglu=True, out=gg)
@@ -615,12 +652,12 @@ class DenoiserEngine:
             y = self._ln(hm, ly.t_attn1.ln, rows=rows, C=C, out=y)
             qkv = self._linear(y, ly.t_attn1.wqkv, M=rows, out=qkv)
             lib.attn_temporal(qkv, qkv[:, C:], qkv[:, 2 * C:], y, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, B=B, F=F, S=S,
-                              heads=t.heads, scale=scale)
+                              heads=t.heads, scale=scale, head_dim=hd)
             self._linear(y, ly.t_attn1.wo, M=rows, bias=ly.t_attn1.bo, res1=hm, out=hm)
             y = self._ln(hm, ly.t_attn2.ln, rows=rows, C=C, out=y)
             q = self._linear(y, ly.t_attn2.wq, M=rows, out=q)
             lib.attn_cross(q, kt, vt, y, ldq=C, ldo=C, rows=rows, heads=t.heads, L=L, F=F, S=S, n_ctx=n_ctx,
-                           temporal=True, batch_offset=batch_offset, scale=scale)
+                           temporal=True, batch_offset=batch_offset, scale=scale, head_dim=hd)
             self._linear(y, ly.t_attn2.wo, M=rows, bias=ly.t_attn2.bo, res1=hm, out=hm)
             y = self._ln(hm, ly.t_ff.ln, rows=rows, C=C, out=y)
             gg = self._linear(y, ly.t_ff.w1, M=rows, bias=ly.t_ff.b1, geglu=True, out=gg)

@@ -50,7 +50,7 @@ class XAttnParams(C.Structure):
         ("q", c_void_p), ("kc", c_void_p), ("vc", c_void_p), ("out", c_void_p),
         ("ldq", c_int), ("ldo", c_int), ("rows", c_int), ("heads", c_int), ("L", c_int),
         ("F", c_int), ("S", c_int), ("n_ctx", c_int), ("temporal", c_int), ("batch_offset", c_int),
-        ("scale", c_float),
+        ("scale", c_float), ("head_dim", c_int),
     ]
 
 
@@ -58,7 +58,7 @@ class TAttnParams(C.Structure):
     _fields_ = [
         ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("out", c_void_p),
         ("ldq", c_int), ("ldk", c_int), ("ldv", c_int), ("ldo", c_int),
-        ("B", c_int), ("F", c_int), ("S", c_int), ("heads", c_int), ("scale", c_float),
+        ("B", c_int), ("F", c_int), ("S", c_int), ("heads", c_int), ("scale", c_float), ("head_dim", c_int),
     ]
 
 
@@ -311,19 +311,21 @@ def attn_spatial(q, k, v, out, *, ldq, ldk, ldv, ldo, n_img, heads, seq, scale) 
     call("ttvdm_attn_spatial", p)
 
 
-def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale) -> None:
+def attn_cross(q, kc, vc, out, *, ldq, ldo, rows, heads, L, F, S, n_ctx, temporal, batch_offset, scale,
+               head_dim=64) -> None:
     p = XAttnParams()
     p.q, p.kc, p.vc, p.out = _ptr(q), _ptr(kc), _ptr(vc), _ptr(out)
     p.ldq, p.ldo, p.rows, p.heads, p.L = ldq, ldo, rows, heads, L
     p.F, p.S, p.n_ctx, p.temporal, p.batch_offset, p.scale = F, S, n_ctx, int(temporal), batch_offset, scale
+    p.head_dim = head_dim
     call("ttvdm_attn_cross", p)
 
 
-def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale) -> None:
+def attn_temporal(q, k, v, out, *, ldq, ldk, ldv, ldo, B, F, S, heads, scale, head_dim=64) -> None:
     p = TAttnParams()
     p.q, p.k, p.v, p.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
     p.ldq, p.ldk, p.ldv, p.ldo = ldq, ldk, ldv, ldo
-    p.B, p.F, p.S, p.heads, p.scale = B, F, S, heads, scale
+    p.B, p.F, p.S, p.heads, p.scale, p.head_dim = B, F, S, heads, scale, head_dim
     call("ttvdm_attn_temporal", p)
 
 

@@ -105,35 +105,35 @@ def case_attn_spatial(n=3, heads=5, S=384, seed=0):
     return rel_l2(out, ref)
 
 
-def case_attn_cross(B=2, F=3, S=96, heads=5, L=78, temporal=False, batch_offset=0, n_ctx=2, seed=0):
-    C = heads * 64
+def case_attn_cross(B=2, F=3, S=96, heads=5, L=78, temporal=False, batch_offset=0, n_ctx=2, seed=0, hd=64):
+    C = heads * hd
     rows = B * F * S
     q = bf(g(rows, C, seed=seed))
     kc = bf(g(n_ctx, L, C, seed=seed + 1))
     vc = bf(g(n_ctx, L, C, seed=seed + 2))
     out = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
     lib.attn_cross(q, kc, vc, out, ldq=C, ldo=C, rows=rows, heads=heads, L=L, F=F, S=S, n_ctx=n_ctx,
-                   temporal=temporal, batch_offset=batch_offset, scale=0.125)
+                   temporal=temporal, batch_offset=batch_offset, scale=hd ** -0.5, head_dim=hd)
     r = torch.arange(rows, device=DEV)
     b = r // (F * S) + batch_offset
     s = r % S
     ctx = ((b * S + s) % n_ctx) if temporal else b
-    qh = q.float().reshape(rows, heads, 1, 64)
-    kh = kc.float()[ctx].reshape(rows, L, heads, 64).transpose(1, 2)
-    vh = vc.float()[ctx].reshape(rows, L, heads, 64).transpose(1, 2)
+    qh = q.float().reshape(rows, heads, 1, hd)
+    kh = kc.float()[ctx].reshape(rows, L, heads, hd).transpose(1, 2)
+    vh = vc.float()[ctx].reshape(rows, L, heads, hd).transpose(1, 2)
     ref = Fn.scaled_dot_product_attention(qh, kh, vh).reshape(rows, C)
     torch.cuda.synchronize()
     return rel_l2(out, ref)
 
 
-def case_attn_temporal(B=2, F=14, S=40, heads=5, seed=0):
-    C = heads * 64
+def case_attn_temporal(B=2, F=14, S=40, heads=5, seed=0, hd=64):
+    C = heads * hd
     rows = B * F * S
     qkv = bf(g(rows, 3 * C, seed=seed))
     out = torch.empty(rows, C, dtype=torch.bfloat16, device=DEV)
     lib.attn_temporal(qkv, qkv[:, C:], qkv[:, 2 * C:], out, ldq=3 * C, ldk=3 * C, ldv=3 * C, ldo=C, B=B, F=F, S=S,
-                      heads=heads, scale=0.125)
-    q, k, v = [t.float().reshape(B, F, S, heads, 64).permute(0, 2, 3, 1, 4) for t in qkv.split(C, dim=1)]
+                      heads=heads, scale=hd ** -0.5, head_dim=hd)
+    q, k, v = [t.float().reshape(B, F, S, heads, hd).permute(0, 2, 3, 1, 4) for t in qkv.split(C, dim=1)]
     ref = Fn.scaled_dot_product_attention(q, k, v).permute(0, 3, 1, 2, 4).reshape(rows, C)
     torch.cuda.synchronize()
     return rel_l2(out, ref)
@@ -421,6 +421,12 @@ CASES = [
     ("attn_cross_temporal_tc_oddS_shard", lambda: case_attn_cross(B=1, F=3, S=1101, heads=2, L=77, temporal=True, batch_offset=1)),
     ("attn_cross_spatial_tc_L128_shard", lambda: case_attn_cross(B=1, F=2, S=520, heads=3, L=128, batch_offset=1)),
     ("attn_cross_spatial_tc_L1", lambda: case_attn_cross(B=2, F=1, S=512, heads=2, L=1)),
+    # head_dim 128 (reference class-default heads at level 2): warp-level kernels, templated on the head dim
+    ("attn_cross_spatial_hd128", lambda: case_attn_cross(B=2, F=3, S=96, heads=3, L=78, hd=128)),
+    ("attn_cross_temporal_hd128_oddS", lambda: case_attn_cross(B=2, F=2, S=135, heads=2, L=77, temporal=True, hd=128)),
+    ("attn_cross_temporal_hd128_big", lambda: case_attn_cross(B=2, F=2, S=1100, heads=2, L=78, temporal=True, hd=128)),
+    ("attn_temporal_hd128", lambda: case_attn_temporal(B=2, F=14, S=37, heads=3, hd=128)),
+    ("attn_temporal_hd128_F4", lambda: case_attn_temporal(B=1, F=4, S=9, heads=2, hd=128)),
     ("attn_temporal", lambda: case_attn_temporal()),
     ("attn_temporal_F16", lambda: case_attn_temporal(B=1, F=16, S=33, heads=2)),
     ("attn_temporal_F3_ragged", lambda: case_attn_temporal(B=2, F=3, S=7, heads=3)),
