@@ -161,7 +161,7 @@ typedef struct {
 int ttvdm_attn_cross(const ttvdm_xattn_params* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K7 — temporal self-attention over the F (<= 16) frames of each (b, s, head); rows ordered (b, f, s),
+ * K7 — temporal self-attention over the F (<= 32) frames of each (b, s, head); rows ordered (b, f, s),
  * i.e. the kernel walks frames with stride S*ld instead of materialising the reference's
  * `(b f) s c -> (b s) f c` permute (diffusers TemporalBasicTransformerBlock.attn1).
  * ------------------------------------------------------------------------------------------------ */

@@ -187,3 +187,15 @@ def test_head_dim_128_compatibility_path_vs_oracle():
         d_ref, m_ref = O.controlnet_forward(state(cn), cfg, sample, T0, ehs, ati, torch.cat([cond[:4], cond[:4]]), 1.0)
         y_ref = O.unet_forward(state(unet), cfg, sample, T0, ehs, ati, d_ref, m_ref)
     assert rel_l2(m, m_ref) < CAP and rel_l2(y, y_ref) < CAP, (rel_l2(m, m_ref), rel_l2(y, y_ref))
+
+
+def test_25_frames_svd_xt_schedule_vs_oracle(tiny):
+    """SVD-XT's 25-frame setting (num_frames is a runtime argument of the reference pipelines): frame positional
+    embeddings, 5-D GroupNorm instances, temporal conv and the temporal attention's two 16-frame tiles."""
+    eu, ec, usd, csd, cfg = tiny
+    sample, ehs, ati, cond = make_inputs(2, 25, 8, 8)
+    with torch.no_grad(), fake_lib.installed():
+        out = eu.unet_forward(sample, T0, ehs, ati)
+        ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
+    assert out.shape == ref.shape == (2, 25, 4, 8, 8)
+    assert rel_l2(out, ref) < CAP

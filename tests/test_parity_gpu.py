@@ -122,6 +122,16 @@ def test_zero_init_gesturenet_equals_vl_on_gpu(tiny):
     assert torch.equal(y1, y2)  # run-to-run determinism of the engine
 
 
+def test_25_frames_svd_xt_on_gpu(tiny):
+    """num_frames = 25 (SVD-XT): the temporal attention kernel's two-tile variant (F <= 32) inside a whole UNet forward."""
+    unet, cn, usd, csd, cfg = tiny
+    sample, ehs, ati, _ = make_inputs(2, 25, 8, 16)
+    with torch.no_grad():
+        y = unet(sample.cuda(), T0.cuda(), ehs.cuda(), ati.cuda()).sample
+        ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
+    assert y.shape == ref.shape and rel_l2(y, ref) < CAP, rel_l2(y, ref)
+
+
 def test_temporal_context_quirk_on_gpu(tiny):
     """Changing context 0 must change batch element 1 only through its EVEN pixels' temporal cross-attention."""
     unet = tiny[0]

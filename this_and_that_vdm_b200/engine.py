@@ -25,7 +25,7 @@ import torch
 from . import lib
 
 BF16 = torch.bfloat16
-MAX_FRAMES = 16  # kTaMaxF of csrc/attn_temporal.cu (one m16 MMA tile of frames per warp)
+MAX_FRAMES = 32  # kTaMaxF of csrc/attn_temporal.cu (two m16 MMA tiles of frames per warp: SVD-XT runs 25)
 PAD_IN = 64  # conv_in channels padded to one 64-wide K chunk
 
 
@@ -804,7 +804,7 @@ class DenoiserEngine:
         B, F, Cin, H, W = sample.shape
         if F > MAX_FRAMES:
             raise lib.TtvdmError(f"num_frames = {F}: the temporal-attention kernel holds at most {MAX_FRAMES} frames per "
-                                 f"sequence (the reference runs 14); SVD-XT's 25-frame setting is not supported")
+                                 f"sequence (the reference runs 14, SVD-XT 25)")
         if H % 8 != 0 or W % 8 != 0:
             raise ValueError(f"latent height/width must be multiples of 8 (3 stride-2 levels), got {H}x{W}")
         if ehs.shape[0] != B:

@@ -64,7 +64,7 @@ class FusedDenoiser:
             raise ValueError(f"latent height/width must be multiples of 8, got {height}x{width}")
         if num_frames > MAX_FRAMES:
             raise lib.TtvdmError(f"num_frames = {num_frames}: the temporal-attention kernel holds at most {MAX_FRAMES} "
-                                 f"frames per sequence (the reference runs 14); SVD-XT's 25-frame setting is not supported")
+                                 f"frames per sequence (the reference runs 14, SVD-XT 25)")
         self.sigmas = [float(s) for s in sigmas]
         n = len(self.sigmas) - 1
         self.n_steps = n

@@ -427,6 +427,10 @@ CASES = [
     ("attn_cross_temporal_hd128_big", lambda: case_attn_cross(B=2, F=2, S=1100, heads=2, L=78, temporal=True, hd=128)),
     ("attn_temporal_hd128", lambda: case_attn_temporal(B=2, F=14, S=37, heads=3, hd=128)),
     ("attn_temporal_hd128_F4", lambda: case_attn_temporal(B=1, F=4, S=9, heads=2, hd=128)),
+    ("attn_temporal_F25_svd_xt", lambda: case_attn_temporal(B=2, F=25, S=21, heads=5)),
+    ("attn_temporal_F17", lambda: case_attn_temporal(B=1, F=17, S=10, heads=2)),
+    ("attn_temporal_F32", lambda: case_attn_temporal(B=1, F=32, S=6, heads=3)),
+    ("attn_temporal_F25_hd128", lambda: case_attn_temporal(B=1, F=25, S=11, heads=2, hd=128)),
     ("attn_temporal", lambda: case_attn_temporal()),
     ("attn_temporal_F16", lambda: case_attn_temporal(B=1, F=16, S=33, heads=2)),
     ("attn_temporal_F3_ragged", lambda: case_attn_temporal(B=2, F=3, S=7, heads=3)),
