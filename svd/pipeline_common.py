@@ -265,7 +265,16 @@ class SVDPipelineBase:
                  timesteps, controlnet=None, controlnet_cond=None, cond_scales=None, callback_on_step_end=None,
                  callback_on_step_end_tensor_inputs=("latents",)):
         """latents [N, F, 4, h, w] (already x init_noise_sigma). Each video n is an independent CFG pair
-        (encoder_hidden_states / image_latents rows [n] = uncond half, [N + n] = cond half)."""
+        (encoder_hidden_states / image_latents rows [n] = uncond half, [N + n] = cond half).
+
+        Two things to know for N > 1 (the reference's callers always run N = 1; the VGL pipeline rejects N > 1 like the
+        reference does):
+          * the reference runs ONE batch of 2N sequences, so its temporal cross-attention quirk
+            (svd/diffusion_arch/transformer_temporal.py:310-319) indexes the context by (b*S + s) mod 2N and mixes the
+            contexts of DIFFERENT videos; here every video is its own pair (mod 2), i.e. the N = 1 behaviour of the
+            reference for each video — results differ from the reference's batched call for N > 1 (DESIGN.md section 1);
+          * with num_videos_per_prompt > 1 the reference lays image_latents out as repeat([neg, lat]) = [neg, lat, neg, lat]
+            and still reads rows [n] / [N + n]; _encode_vae_image reproduces that layout, so the same rows are paired."""
         from this_and_that_vdm_b200.sampler import FusedDenoiser
         dev = latents.device
         N = latents.shape[0]
