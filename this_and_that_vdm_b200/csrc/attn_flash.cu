@@ -48,7 +48,7 @@ constexpr int kD = 64;        // head dim
 constexpr int kKV = 4;        // K/V ring depth
 constexpr int kTileBytes = 128 * 64 * 2;  // 16 KB
 constexpr int kAttnThreads = 128 + 128 * kQTiles;  // 4 service warps + 4 softmax warps per Q tile
-constexpr int kAttnPolyDefault = 3;  // of every 8 column pairs (see attn_flash_kernel)
+constexpr int kAttnPolyDefault = 13;  // 3 of every 8 column pairs, spread (TTVDM_ATTN_POLY: 0..4 = first n of 8, 12..14 = n - 10 spread)
 constexpr int kAttnSmem = kTileBytes * (2 * kQTiles + 2 * kKV) + 512;
 // TMEM columns: S_0 [0,128)  S_1 [128,256)  O_0 [256,320)  O_1 [320,384)  P_0 [384,448)  P_1 [448,512)
 constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& r0, fl
 // one (b, f) unit fetched by a 3-D TMA box whose row dimension has element stride q_stride — for the temporal layers
 // that gathers exactly the rows s = s0 + n_ctx * i that read this context (the reference's quirk,
 // svd/diffusion_arch/transformer_temporal.py:310-319), so nothing is masked or computed twice.
-template <int kPoly, bool kCross>
+template <int kPoly, bool kCross, bool kSpread = false>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs g) {
@@ -401,7 +401,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             float x0, x1, p0, p1;
             unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(v[cc][i]), __uint_as_float(v[cc][i + 1])), c22, nms2), x0, x1);
             // a ragged (masked) KV tile is rare and CTA-uniform: it keeps every exponential on the MUFU
-            if (((i >> 1) & 7) < kPoly && !masked) {
+            // kSpread: the kPoly polynomial pairs of every 8 are spread evenly (Bresenham: 3 of 8 = pairs 0, 3, 6) instead of
+            // being the first kPoly — MUFU and FMA-pipe work alternate at a finer grain in the instruction stream
+            if ((kSpread ? ((((i >> 1) & 7) * kPoly) & 7) : ((i >> 1) & 7)) < kPoly && !masked) {
               exp2_poly_pair(x0, x1, p0, p1);
             } else {
               p0 = ex2(x0);  // exp2(-inf) = 0 for masked keys
@@ -484,14 +486,17 @@ static int launch_attn(const void* q, int ldq, long long q_rows, const void* k, 
     if ((rc = make_tmap_bf16(&tmV, v, 2, dims, strv, box))) return rc;
   }
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnArgs);
-  static const Kern kerns[6] = {attn_flash_kernel<0, false>, attn_flash_kernel<1, false>, attn_flash_kernel<2, false>,
-                                attn_flash_kernel<3, false>, attn_flash_kernel<4, false>, attn_flash_kernel<0, true>};
+  static const Kern kerns[9] = {attn_flash_kernel<0, false>, attn_flash_kernel<1, false>, attn_flash_kernel<2, false>,
+                                attn_flash_kernel<3, false>, attn_flash_kernel<4, false>, attn_flash_kernel<0, true>,
+                                attn_flash_kernel<2, false, true>, attn_flash_kernel<3, false, true>,
+                                attn_flash_kernel<4, false, true>};
   static int poly = -1;  // column pairs of every 8 whose exponential runs on the FMA pipe (TTVDM_ATTN_POLY: A/B runs)
   if (poly < 0) {
     const char* e = getenv("TTVDM_ATTN_POLY");
-    int v = e ? atoi(e) : kAttnPolyDefault;
-    if (v < 0 || v > 4) v = kAttnPolyDefault;
-    for (int i = 0; i < 6; ++i) {
+    int v = e ? atoi(e) : kAttnPolyDefault;  // 0..4: first v pairs of every 8; 12..14: v - 10 pairs spread over every 8
+    if (!((v >= 0 && v <= 4) || (v >= 12 && v <= 14))) v = kAttnPolyDefault;
+    if (v >= 12) v = v - 12 + 6;  // index into kerns[]
+    for (int i = 0; i < 9; ++i) {
       cudaError_t ce = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
       if (ce != cudaSuccess) return fail(TTVDM_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     }
