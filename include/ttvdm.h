@@ -114,6 +114,10 @@ typedef struct {
   const float* ln_rowsums; const float* ln_colsum; float ln_eps;
   const float* prevec; int prevec_rows; int prevec_mod; int ldpv;
   const float* ln_row_add;              /* [prevec_mod][2] or NULL */
+  /* ABI 4. CONV3X3 only: 0 / 1 = stride 1; 2 = stride 2 with padding 1 (diffusers Downsample2D conv): H, W are the OUTPUT
+   * height / width (M = n_img*H*W), A is the [n_img, 2H, 2W, k1] input, read through a TMA box with element stride 2 —
+   * no im2col pass. */
+  int conv_stride;
 } ttvdm_gemm_params;
 
 int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream);

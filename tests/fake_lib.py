@@ -39,7 +39,7 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
          rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None, ldr1=0, s1=1.0, res2=None, ldr2=0, s2=1.0,
          geglu=False, ldo=None, out_fp32=False, act=0, gn_stats_out=None, gn_rows_per_inst=0, row_sums_out=None, rs_addvec=None, rs_add_rows=0, rs_add_mod=0,
          ln_rowsums=None, ln_colsum=None, ln_eps=1e-5, prevec=None, prevec_rows=0, prevec_mod=0, ldpv=0,
-         ln_row_add=None) -> None:
+         ln_row_add=None, conv_stride=1) -> None:
     assert k1 % 64 == 0 and k2 % 64 == 0, "gemm: k1 / k2 must be multiples of 64"
     assert a.dtype == BF16 and w.dtype == BF16
     lda = k1 if lda is None else lda
@@ -52,9 +52,10 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
             A = torch.cat([A, _mat(a2, M, k2, lda2 if lda2 else k2).float()], 1)
         acc = A @ wm.t()
     elif mode == lib.A_CONV3X3:
-        assert n_img * H * W == M and a2 is None
-        x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1).permute(0, 3, 1, 2)
-        acc = Fn.conv2d(x, wm.view(N, 3, 3, k1).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(M, N)
+        assert n_img * H * W == M and a2 is None and conv_stride in (1, 2)
+        cs = conv_stride  # H, W are OUTPUT dims; the input is [n_img, cs*H, cs*W, k1]
+        x = _mat(a, M * cs * cs, k1, lda).float().view(n_img, H * cs, W * cs, k1).permute(0, 3, 1, 2)
+        acc = Fn.conv2d(x, wm.view(N, 3, 3, k1).permute(0, 3, 1, 2), padding=1, stride=cs).permute(0, 2, 3, 1).reshape(M, N)
     else:
         assert n_img * H * W == M and a2 is None  # n_img = B, H = F, W = S
         x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1)

@@ -50,6 +50,7 @@ struct GemmArgs {
   void* out;
   int ldo, out_fp32, act;
   int n_img;          // images (CONV) / batch (TCONV): tiles beyond it are padding of an odd CTA pair
+  int conv_stride;    // CONV3X3: 1 or 2 (input coordinates = stride * output coordinates + tap offset)
   int b_resident;     // 1: this CTA keeps ONE N tile of W (all K chunks) in smem and only streams A tiles
   int ctas_per_n;     // b_resident: CTAs sharing an N tile
   int tma_epi;        // 1: residual tile in / output tile out through per-warp smem + TMA (coalesced, asynchronous)
@@ -530,8 +531,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             else tma_load_2d_pair(sa, ma, &full_bar[stage], ck, t.m0);
           } else if (g.mode == TTVDM_A_CONV3X3) {
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
-            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0 + dx, t.h0 + dy, t.img);
+            const int cs = g.conv_stride;
+            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
+            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
           } else {
             if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
             else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
@@ -1074,6 +1076,7 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     return fail(TTVDM_ERR_SHAPE, "gemm: prevec must be 16 B aligned with ldpv %% 4 == 0");
 
   GemmArgs g;
+  g.conv_stride = 1;
   memset(&g, 0, sizeof(g));
   g.mode = p->mode;
   g.M = p->M;
@@ -1176,10 +1179,18 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
     g.tiles_w = (p->W + g.TW - 1) / g.TW;
     g.tiles_h = (p->H + g.TH - 1) / g.TH;
     g.m_tiles = p->n_img * g.tiles_w * g.tiles_h;
-    uint64_t dims[4] = {(uint64_t)p->k1, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->n_img};
-    uint64_t str[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * p->W, (uint64_t)p->lda * 2 * p->W * p->H};
-    uint32_t box[4] = {kBlockK, (uint32_t)g.TW, (uint32_t)g.TH, 1};
-    if ((rc = make_tmap_bf16(&tmA, p->a, 4, dims, str, box))) return rc;
+    const int cs = p->conv_stride == 2 ? 2 : 1;
+    if (p->conv_stride != 0 && p->conv_stride != 1 && p->conv_stride != 2)
+      return fail(TTVDM_ERR_SHAPE, "conv3x3: stride %d (1 or 2)", p->conv_stride);
+    g.conv_stride = cs;
+    // stride 2: the input is [n_img, 2H, 2W, k1]; a box of (2 TW) x (2 TH) positions with element stride 2 delivers the
+    // TW x TH pixels one tap needs (negative / past-the-end coordinates are zero-filled: the padding of 1)
+    const uint64_t Wi = (uint64_t)p->W * cs, Hi = (uint64_t)p->H * cs;
+    uint64_t dims[4] = {(uint64_t)p->k1, Wi, Hi, (uint64_t)p->n_img};
+    uint64_t str[3] = {(uint64_t)p->lda * 2, (uint64_t)p->lda * 2 * Wi, (uint64_t)p->lda * 2 * Wi * Hi};
+    uint32_t box[4] = {kBlockK, (uint32_t)(g.TW * cs), (uint32_t)(g.TH * cs), 1};
+    uint32_t est[4] = {1, (uint32_t)cs, (uint32_t)cs, 1};
+    if ((rc = make_tmap_bf16(&tmA, p->a, 4, dims, str, box, true, est))) return rc;
     tmA2 = tmA;
   } else if (p->mode == TTVDM_A_TCONV3) {
     if ((long long)p->n_img * p->H * p->W != p->M) return fail(TTVDM_ERR_SHAPE, "tconv3: M != B*F*S");

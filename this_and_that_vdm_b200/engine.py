@@ -441,14 +441,15 @@ class DenoiserEngine:
         return out
 
     def _conv3(self, x, w, bias, *, n_img, H, W, cin, out=None, rowvec=None, rows_per_vec=0, ldrv=0, res1=None,
-               out_fp32=False, gn_rpi=0):
+               out_fp32=False, gn_rpi=0, stride=1):
+        """3x3 convolution, padding 1. H, W are the OUTPUT dims (stride 2: the input is [n_img, 2H, 2W, cin])."""
         N = w.shape[0]
         M = n_img * H * W
         if out is None:
             out = self._empty(M, N, dtype=torch.float32 if out_fp32 else BF16)
         kw = self._norm_out_kw(out, M, N, gn_rpi, False, None) if not out_fp32 else {}
         lib.gemm(x, w, out, M=M, N=N, k1=cin, mode=lib.A_CONV3X3, n_img=n_img, H=H, W=W, bias=bias, rowvec=rowvec,
-                 rows_per_vec=rows_per_vec, ldrv=ldrv, res1=res1, out_fp32=out_fp32, **kw)
+                 rows_per_vec=rows_per_vec, ldrv=ldrv, res1=res1, out_fp32=out_fp32, conv_stride=stride, **kw)
         return out
 
     def _tconv(self, x, w, bias, *, B, F, S, C, out=None, rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None,
@@ -738,11 +739,13 @@ class DenoiserEngine:
                 skips.append(x)
                 dims.append((H, W))
             if blk["down_w"] is not None:
-                C = x.shape[1]
-                col = self._empty(n_img * (H // 2) * (W // 2), 9 * C)
-                lib.im2col_s2(x, col, n_img=n_img, H=H, W=W, C=C)
+                # Downsample2D: 3x3 conv, stride 2, padding 1 — implicit GEMM over a TMA box with element stride 2 (round 2;
+                # round 1 gathered a 9x im2col buffer first)
                 H, W = H // 2, W // 2
-                x = self._linear(col, blk["down_w"], M=n_img * H * W, bias=blk["down_b"], gn_rpi=H * W)
+                if (2 * H, 2 * W) != dims[-1]:
+                    raise lib.TtvdmError(f"Downsample2D needs even height / width, got {dims[-1]}")
+                x = self._conv3(x, blk["down_w"], blk["down_b"], n_img=n_img, H=H, W=W, cin=x.shape[1], gn_rpi=H * W,
+                                stride=2)
                 skips.append(x)
                 dims.append((H, W))
         return x, skips, dims, ti

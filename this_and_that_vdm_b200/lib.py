@@ -33,7 +33,7 @@ class GemmParams(C.Structure):
         ("rs_addvec", c_void_p), ("rs_add_rows", c_int), ("rs_add_mod", c_int), ("ld_rs_add", c_int),
         ("ln_rowsums", c_void_p), ("ln_colsum", c_void_p), ("ln_eps", c_float),
         ("prevec", c_void_p), ("prevec_rows", c_int), ("prevec_mod", c_int), ("ldpv", c_int),
-        ("ln_row_add", c_void_p),
+        ("ln_row_add", c_void_p), ("conv_stride", c_int),
     ]
 
 
@@ -275,7 +275,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          rs_add_mod: int = 0,
          ln_rowsums: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          prevec: Optional[torch.Tensor] = None, prevec_rows: int = 0, prevec_mod: int = 0, ldpv: int = 0,
-         ln_row_add: Optional[torch.Tensor] = None) -> None:
+         ln_row_add: Optional[torch.Tensor] = None, conv_stride: int = 1) -> None:
     """gn_stats_out: fp64 [M / gn_rows_per_inst, N / 2, 2] (pre-zeroed; the epilogue adds the GroupNorm sums of `out`);
     row_sums_out: fp32 [N / 32, M, 2] (LayerNorm partial sums of `out`, no zeroing needed); ln_rowsums (= the producer's
     row_sums_out, [K / 32, M, 2]) / ln_colsum (+ prevec / ln_row_add):
@@ -300,6 +300,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     p.ln_rowsums, p.ln_colsum, p.ln_eps = _ptr(ln_rowsums), _ptr(ln_colsum), ln_eps
     p.prevec, p.prevec_rows, p.prevec_mod, p.ldpv = _ptr(prevec), prevec_rows, prevec_mod, ldpv if ldpv else N
     p.ln_row_add = _ptr(ln_row_add)
+    p.conv_stride = conv_stride
     call("ttvdm_gemm", p)
 
 

@@ -58,16 +58,17 @@ def case_gemm_linear(M=1000, N=320, K=320, bias=True, res=False, geglu=False, a2
     return rel_l2(out, ref)
 
 
-def case_conv3x3(n=3, H=9, W=16, Cin=64, Cout=64, temb=True, fp32_out=False, seed=0):
-    x = bf(g(n, H, W, Cin, seed=seed))  # NHWC
+def case_conv3x3(n=3, H=9, W=16, Cin=64, Cout=64, temb=True, fp32_out=False, seed=0, stride=1):
+    """H, W: OUTPUT dims; stride 2 (Downsample2D) reads a [n, 2H, 2W, Cin] input."""
+    x = bf(g(n, H * stride, W * stride, Cin, seed=seed))  # NHWC
     w = bf(g(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
     b = g(Cout, seed=seed + 2)
     tv = g(n, Cout, seed=seed + 3) if temb else None
     wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
     out = torch.empty(n * H * W, Cout, dtype=torch.float32 if fp32_out else torch.bfloat16, device=DEV)
     lib.gemm(x, wk, out, M=n * H * W, N=Cout, k1=Cin, mode=lib.A_CONV3X3, n_img=n, H=H, W=W, bias=b, rowvec=tv,
-             rows_per_vec=H * W, out_fp32=fp32_out)
-    ref = Fn.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)
+             rows_per_vec=H * W, out_fp32=fp32_out, conv_stride=stride)
+    ref = Fn.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1, stride=stride)
     if temb:
         ref = ref + tv[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1).reshape(n * H * W, Cout)
@@ -397,6 +398,11 @@ CASES = [
     ("gemm_linear_res_640", lambda: case_gemm_linear(M=128 * 150, N=640, K=640, res=True)),
     ("gemm_linear_multitile", lambda: case_gemm_linear(M=128 * 200, N=1920, K=640, bias=False)),
     ("conv3x3_small", lambda: case_conv3x3()),
+    # Downsample2D: stride 2, padding 1, through a TMA box with element stride 2 (no im2col)
+    ("conv3x3_stride2_small", lambda: case_conv3x3(n=3, H=9, W=16, Cin=64, Cout=64, temb=False, stride=2)),
+    ("conv3x3_stride2_L0", lambda: case_conv3x3(n=2, H=36, W=64, Cin=320, Cout=320, temb=False, stride=2)),
+    ("conv3x3_stride2_odd_tiles", lambda: case_conv3x3(n=2, H=5, W=7, Cin=128, Cout=192, temb=False, stride=2)),
+    ("conv3x3_stride2_L2", lambda: case_conv3x3(n=4, H=9, W=16, Cin=1280, Cout=1280, temb=False, stride=2)),
     ("conv3x3_L0", lambda: case_conv3x3(n=2, H=32, W=48, Cin=320, Cout=320)),
     ("conv3x3_wide", lambda: case_conv3x3(n=1, H=7, W=130, Cin=128, Cout=192)),
     ("conv3x3_out4_fp32", lambda: case_conv3x3(n=2, H=8, W=12, Cin=320, Cout=4, temb=False, fp32_out=True)),
