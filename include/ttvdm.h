@@ -118,6 +118,11 @@ typedef struct {
    * height / width (M = n_img*H*W), A is the [n_img, 2H, 2W, k1] input, read through a TMA box with element stride 2 —
    * no im2col pass. */
   int conv_stride;
+  /* ABI 4. CONV3X3 only: conv_taps = 0 / 9: the 3 x 3 taps (dy, dx in -1..1). conv_taps = 4: a 2 x 2 window whose first
+   * tap sits at (conv_dy0, conv_dx0) relative to the output pixel, W = [N, 4*k1] — one of the four parity convolutions
+   * that nearest-x2 upsampling followed by a 3 x 3 convolution (diffusers Upsample2D) decomposes into on the LOW-resolution
+   * input (16 instead of 36 tap-pixels); ttvdm_interleave2x puts the four results into place. */
+  int conv_taps, conv_dy0, conv_dx0;
 } ttvdm_gemm_params;
 
 int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream);
@@ -224,6 +229,8 @@ int ttvdm_layernorm(const ttvdm_layernorm_params* p, void* stream);
  * ------------------------------------------------------------------------------------------------ */
 int ttvdm_im2col_s2(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
 int ttvdm_upsample2x(const void* x, void* out, int n_img, int H, int W, int C, void* stream);
+/* parts: bf16 [4][n_img, H, W, C], parity p = 2*py + px  ->  out bf16 [n_img, 2H, 2W, C], out[n, 2y+py, 2x+px] = parts[p][n, y, x] */
+int ttvdm_interleave2x(const void* parts, void* out, int n_img, int H, int W, int C, void* stream);
 /* K13 helper: out[i, :] = [cos(t_i * w_j) | sin(t_i * w_j)], w_j = exp(-ln(1e4) * j / (dim/2)) — diffusers
  * Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0); t fp32 [n] on device, out bf16 [n, dim]. */
 int ttvdm_sinusoid(const float* t, void* out, int n, int dim, void* stream);

@@ -39,11 +39,13 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
          rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None, ldr1=0, s1=1.0, res2=None, ldr2=0, s2=1.0,
          geglu=False, ldo=None, out_fp32=False, act=0, gn_stats_out=None, gn_rows_per_inst=0, row_sums_out=None, rs_addvec=None, rs_add_rows=0, rs_add_mod=0,
          ln_rowsums=None, ln_colsum=None, ln_eps=1e-5, prevec=None, prevec_rows=0, prevec_mod=0, ldpv=0,
-         ln_row_add=None, conv_stride=1) -> None:
+         ln_row_add=None, conv_stride=1, conv_taps=0, conv_dy0=0, conv_dx0=0) -> None:
     assert k1 % 64 == 0 and k2 % 64 == 0, "gemm: k1 / k2 must be multiples of 64"
     assert a.dtype == BF16 and w.dtype == BF16
     lda = k1 if lda is None else lda
     taps = {lib.A_LINEAR: 1, lib.A_CONV3X3: 9, lib.A_TCONV3: 3}[mode]
+    if mode == lib.A_CONV3X3 and conv_taps == 4:
+        taps = 4
     ktot = taps * (k1 + k2)
     wm = _mat(w, N, ktot, ktot).float()
     if mode == lib.A_LINEAR:
@@ -55,7 +57,14 @@ def gemm(a, w, out, *, M, N, k1, mode=lib.A_LINEAR, lda=None, a2=None, k2=0, lda
         assert n_img * H * W == M and a2 is None and conv_stride in (1, 2)
         cs = conv_stride  # H, W are OUTPUT dims; the input is [n_img, cs*H, cs*W, k1]
         x = _mat(a, M * cs * cs, k1, lda).float().view(n_img, H * cs, W * cs, k1).permute(0, 3, 1, 2)
-        acc = Fn.conv2d(x, wm.view(N, 3, 3, k1).permute(0, 3, 1, 2), padding=1, stride=cs).permute(0, 2, 3, 1).reshape(M, N)
+        if taps == 4:
+            # 2 x 2 window whose first tap sits at (conv_dy0, conv_dx0): embed it in a 3 x 3 kernel
+            assert cs == 1 and conv_dy0 in (-1, 0) and conv_dx0 in (-1, 0)
+            k3 = torch.zeros(N, 3, 3, k1)
+            k3[:, conv_dy0 + 1:conv_dy0 + 3, conv_dx0 + 1:conv_dx0 + 3] = wm.view(N, 2, 2, k1)
+        else:
+            k3 = wm.view(N, 3, 3, k1)
+        acc = Fn.conv2d(x, k3.permute(0, 3, 1, 2), padding=1, stride=cs).permute(0, 2, 3, 1).reshape(M, N)
     else:
         assert n_img * H * W == M and a2 is None  # n_img = B, H = F, W = S
         x = _mat(a, M, k1, lda).float().view(n_img, H, W, k1)
@@ -217,6 +226,12 @@ def im2col_s2(x, out, *, n_img, H, W, C) -> None:
     _count()
 
 
+def interleave2x(parts, out, *, n_img, H, W, C) -> None:
+    pp = _mat(parts, 4 * n_img * H * W, C, C).view(2, 2, n_img, H, W, C)  # [py, px, n, y, x, c]
+    _mat(out, n_img * 4 * H * W, C, C).copy_(pp.permute(2, 3, 0, 4, 1, 5).reshape(n_img * 4 * H * W, C))
+    _count()
+
+
 def upsample2x(x, out, *, n_img, H, W, C) -> None:
     xi = _mat(x, n_img * H * W, C, C).view(n_img, H, W, C)
     up = xi.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(n_img * 4 * H * W, C)
@@ -348,7 +363,7 @@ def launch_count() -> int:
 
 _PATCHED = ["gemm", "attn_spatial", "attn_cross", "attn_temporal", "groupnorm", "layernorm", "im2col_s2", "upsample2x",
             "sinusoid", "axpy", "sampler_prepare", "sampler_euler_step", "softmax_rows", "im2col_s2_pad01",
-            "vae_time_conv_out", "act_inplace", "layernorm_flat", "launch_count", "pack_conv_weight", "pack_linear",
+            "vae_time_conv_out", "interleave2x", "act_inplace", "layernorm_flat", "launch_count", "pack_conv_weight", "pack_linear",
             "pack_vector"]
 
 

@@ -50,6 +50,7 @@ struct GemmArgs {
   void* out;
   int ldo, out_fp32, act;
   int n_img;          // images (CONV) / batch (TCONV): tiles beyond it are padding of an odd CTA pair
+  int tap_w, dy0, dx0; // CONV3X3: taps per window row (3, or 2 for the parity convolutions) and offset of the first tap
   int conv_stride;    // CONV3X3: 1 or 2 (input coordinates = stride * output coordinates + tap offset)
   int b_resident;     // 1: this CTA keeps ONE N tile of W (all K chunks) in smem and only streams A tiles
   int ctas_per_n;     // b_resident: CTAs sharing an N tile
@@ -530,7 +531,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (kCtas == 1) tma_load_2d(sa, ma, &full_bar[stage], ck, t.m0);
             else tma_load_2d_pair(sa, ma, &full_bar[stage], ck, t.m0);
           } else if (g.mode == TTVDM_A_CONV3X3) {
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const int ty = tap / g.tap_w;
+            const int dy = ty + g.dy0, dx = tap - ty * g.tap_w + g.dx0;
             const int cs = g.conv_stride;
             if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
             else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
@@ -1077,6 +1079,8 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
 
   GemmArgs g;
   g.conv_stride = 1;
+  g.tap_w = 3;
+  g.dy0 = g.dx0 = -1;
   memset(&g, 0, sizeof(g));
   g.mode = p->mode;
   g.M = p->M;
@@ -1084,6 +1088,17 @@ extern "C" int ttvdm_gemm(const ttvdm_gemm_params* p, void* stream_) {
   g.kc_a1 = p->k1 / kBlockK;
   g.kc_per_tap = (p->k1 + k2) / kBlockK;
   g.taps = p->mode == TTVDM_A_CONV3X3 ? 9 : (p->mode == TTVDM_A_TCONV3 ? 3 : 1);
+  g.tap_w = 3;
+  g.dy0 = g.dx0 = -1;
+  if (p->mode == TTVDM_A_CONV3X3 && p->conv_taps == 4) {
+    if (p->conv_stride == 2) return fail(TTVDM_ERR_SHAPE, "conv3x3: the 2 x 2 window is a stride-1 mode");
+    g.taps = 4;
+    g.tap_w = 2;
+    g.dy0 = p->conv_dy0;
+    g.dx0 = p->conv_dx0;
+  } else if (p->mode == TTVDM_A_CONV3X3 && p->conv_taps != 0 && p->conv_taps != 9) {
+    return fail(TTVDM_ERR_SHAPE, "conv3x3: conv_taps %d (0 / 9 or 4)", p->conv_taps);
+  }
   g.block_n = pick_block_n(p->N);
   const int ktot_pre = g.taps * (p->k1 + k2);
   int want_tma = 0;

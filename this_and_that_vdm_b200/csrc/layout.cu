@@ -41,6 +41,24 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
   }
 }
 
+// out[n, 2y+py, 2x+px, :] = parts[2*py+px][n, y, x, :]  (16-byte pieces; the write side is the contiguous one)
+__global__ void interleave2x_kernel(const uint4* __restrict__ parts, uint4* __restrict__ out, int n_img, int H, int W,
+                                    int C8) {
+  const long long plane = (long long)n_img * H * W * C8;
+  const long long total = 4 * plane;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int ho = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    const int p = ((ho & 1) << 1) | (wo & 1);
+    out[i] = __ldg(parts + p * plane + (((long long)n * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+  }
+}
+
 __global__ void axpy_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                             float scale, long long n8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -143,6 +161,16 @@ extern "C" int ttvdm_upsample2x(const void* x, void* out, int n_img, int H, int 
   upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, H, W, C / 8);
   TTVDM_CHECK_LAUNCH("upsample2x_kernel");
+  return 0;
+}
+
+extern "C" int ttvdm_interleave2x(const void* parts, void* out, int n_img, int H, int W, int C, void* stream_) {
+  if (int rc = ensure_init()) return rc;
+  if (!parts || !out || C % 8 != 0 || n_img <= 0) return fail(TTVDM_ERR_SHAPE, "interleave2x: need C%%8==0 (C=%d)", C);
+  const long long total = (long long)n_img * H * 2 * W * 2 * (C / 8);
+  interleave2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(parts), static_cast<uint4*>(out), n_img, H, W, C / 8);
+  TTVDM_CHECK_LAUNCH("interleave2x_kernel");
   return 0;
 }
 

@@ -65,6 +65,26 @@ def _pack_conv(w: torch.Tensor, dev, pad_cin: int = 0) -> torch.Tensor:
     return out
 
 
+def _pack_upsample_parity(w: torch.Tensor, dev) -> List[torch.Tensor]:
+    """Conv2d weight [Cout, Cin, 3, 3] of an Upsample2D -> four bf16 [Cout, 4 * Cin] operands, parity p = 2 * py + px:
+    after nearest x2, output row 2y + py reads source rows {y - 1: ky 0, y: ky 1 + 2} (py = 0) or {y: ky 0 + 1, y + 1: ky 2}
+    (py = 1), likewise for columns, so the 3x3 taps collapse into a 2x2 window with summed weights (summed in fp32 on the
+    host, then packed like any conv weight)."""
+    w = w.detach().to("cpu", torch.float32)
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            wp = torch.zeros(w.shape[0], w.shape[1], 2, 2)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    for ky in groups[py][ty]:
+                        for kx in groups[px][tx]:
+                            wp[:, :, ty, tx] += w[:, :, ky, kx]
+            out.append(_pack_conv(wp, dev))
+    return out
+
+
 _pack_conv3x3 = _pack_conv
 _pack_tconv = _pack_conv
 
@@ -343,6 +363,7 @@ class DenoiserEngine:
                     j += 1
                 if f"{p}.upsamplers.0.conv.weight" in sd:
                     blk["up_w"] = _pack_conv3x3(g(f"{p}.upsamplers.0.conv.weight"), dev)
+                    blk["up_wp"] = _pack_upsample_parity(g(f"{p}.upsamplers.0.conv.weight"), dev)
                     blk["up_b"] = _f32(g(f"{p}.upsamplers.0.conv.bias"), dev)
                 self.up.append(blk)
             self.out_g, self.out_b = _f32(g("conv_norm_out.weight"), dev), _f32(g("conv_norm_out.bias"), dev)
@@ -450,6 +471,29 @@ class DenoiserEngine:
         kw = self._norm_out_kw(out, M, N, gn_rpi, False, None) if not out_fp32 else {}
         lib.gemm(x, w, out, M=M, N=N, k1=cin, mode=lib.A_CONV3X3, n_img=n_img, H=H, W=W, bias=bias, rowvec=rowvec,
                  rows_per_vec=rows_per_vec, ldrv=ldrv, res1=res1, out_fp32=out_fp32, conv_stride=stride, **kw)
+        return out
+
+    def _upsample_conv(self, x, blk, *, n_img, H, W):
+        """Upsample2D = nearest x2 + 3x3 conv, WITHOUT the upsampled tensor: every output parity (py, px) is a 2x2-tap
+        convolution of the LOW-resolution input with pre-summed weights (_pack_upsample_parity) — 16 instead of 36
+        tap-pixels — and ttvdm_interleave2x puts the four results into place. The GroupNorm sums of the next ResBlock are
+        accumulated by the four epilogues into one buffer (an instance is a frame either way)."""
+        C = x.shape[1]
+        N = blk["up_wp"][0].shape[0]
+        M = n_img * H * W
+        out = self._empty(4 * M, N)
+        parts = self._empty(4, M, N)
+        out.ln_sums = None
+        out.gn_stats = None
+        kw = {}
+        if self.fuse_norm_stats and N % 64 == 0:
+            st = self._stat(n_img * N, torch.float64)
+            kw = dict(gn_stats_out=st, gn_rows_per_inst=H * W)
+            out.gn_stats = (st, 4 * H * W)
+        for pi, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+            lib.gemm(x, blk["up_wp"][pi], parts[pi], M=M, N=N, k1=C, mode=lib.A_CONV3X3, n_img=n_img, H=H, W=W,
+                     bias=blk["up_b"], conv_taps=4, conv_dy0=py - 1, conv_dx0=px - 1, **kw)
+        lib.interleave2x(parts, out, n_img=n_img, H=H, W=W, C=N)
         return out
 
     def _tconv(self, x, w, bias, *, B, F, S, C, out=None, rowvec=None, rows_per_vec=0, ldrv=0, s0=1.0, res1=None,
@@ -769,11 +813,15 @@ class DenoiserEngine:
                                           batch_offset=batch_offset)
                     ti += 1
             if blk["up_w"] is not None:
-                C = x.shape[1]
-                up = self._empty(n_img * 4 * H * W, C)
-                lib.upsample2x(x, up, n_img=n_img, H=H, W=W, C=C)
-                H, W = 2 * H, 2 * W
-                x = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n_img, H=H, W=W, cin=C, gn_rpi=H * W)
+                if os.environ.get("TTVDM_UPSAMPLE_PARITY", "1") != "0":
+                    x = self._upsample_conv(x, blk, n_img=n_img, H=H, W=W)
+                    H, W = 2 * H, 2 * W
+                else:  # A/B: materialise the upsampled tensor, then the 3x3 conv (round 1's schedule)
+                    C = x.shape[1]
+                    up = self._empty(n_img * 4 * H * W, C)
+                    lib.upsample2x(x, up, n_img=n_img, H=H, W=W, C=C)
+                    H, W = 2 * H, 2 * W
+                    x = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n_img, H=H, W=W, cin=C, gn_rpi=H * W)
         rows = n_img * H * W
         y = self._gn(x, self.out_g, self.out_b, rows=rows, rows_per_inst=H * W, eps=1e-5, silu=True)
         return self._conv3(y, self.conv_out_w, self.conv_out_b, n_img=n_img, H=H, W=W, cin=x.shape[1], out_fp32=True)

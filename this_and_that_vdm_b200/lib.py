@@ -33,7 +33,8 @@ class GemmParams(C.Structure):
         ("rs_addvec", c_void_p), ("rs_add_rows", c_int), ("rs_add_mod", c_int), ("ld_rs_add", c_int),
         ("ln_rowsums", c_void_p), ("ln_colsum", c_void_p), ("ln_eps", c_float),
         ("prevec", c_void_p), ("prevec_rows", c_int), ("prevec_mod", c_int), ("ldpv", c_int),
-        ("ln_row_add", c_void_p), ("conv_stride", c_int),
+        ("ln_row_add", c_void_p), ("conv_stride", c_int), ("conv_taps", c_int), ("conv_dy0", c_int),
+        ("conv_dx0", c_int),
     ]
 
 
@@ -128,7 +129,7 @@ EXPORTS = [
     "ttvdm_groupnorm_workspace_bytes", "ttvdm_gemm_gn_stats_bytes", "ttvdm_gemm_row_sums_bytes",
     "ttvdm_gemm_workspace_bytes", "ttvdm_attn_workspace_bytes", "ttvdm_gesture_scratch_bytes",
     "ttvdm_gemm", "ttvdm_attn_spatial", "ttvdm_attn_cross", "ttvdm_attn_temporal",
-    "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_axpy", "ttvdm_sinusoid",
+    "ttvdm_groupnorm", "ttvdm_layernorm", "ttvdm_im2col_s2", "ttvdm_upsample2x", "ttvdm_interleave2x", "ttvdm_axpy", "ttvdm_sinusoid",
     "ttvdm_sampler_prepare", "ttvdm_sampler_euler_step", "ttvdm_gesture_raster",
     "ttvdm_softmax_rows", "ttvdm_im2col_s2_pad01", "ttvdm_vae_time_conv_out",
     "ttvdm_act_inplace", "ttvdm_layernorm_flat",
@@ -275,7 +276,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          rs_add_mod: int = 0,
          ln_rowsums: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          prevec: Optional[torch.Tensor] = None, prevec_rows: int = 0, prevec_mod: int = 0, ldpv: int = 0,
-         ln_row_add: Optional[torch.Tensor] = None, conv_stride: int = 1) -> None:
+         ln_row_add: Optional[torch.Tensor] = None, conv_stride: int = 1, conv_taps: int = 0, conv_dy0: int = 0,
+         conv_dx0: int = 0) -> None:
     """gn_stats_out: fp64 [M / gn_rows_per_inst, N / 2, 2] (pre-zeroed; the epilogue adds the GroupNorm sums of `out`);
     row_sums_out: fp32 [N / 32, M, 2] (LayerNorm partial sums of `out`, no zeroing needed); ln_rowsums (= the producer's
     row_sums_out, [K / 32, M, 2]) / ln_colsum (+ prevec / ln_row_add):
@@ -300,7 +302,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     p.ln_rowsums, p.ln_colsum, p.ln_eps = _ptr(ln_rowsums), _ptr(ln_colsum), ln_eps
     p.prevec, p.prevec_rows, p.prevec_mod, p.ldpv = _ptr(prevec), prevec_rows, prevec_mod, ldpv if ldpv else N
     p.ln_row_add = _ptr(ln_row_add)
-    p.conv_stride = conv_stride
+    p.conv_stride, p.conv_taps, p.conv_dy0, p.conv_dx0 = conv_stride, conv_taps, conv_dy0, conv_dx0
     call("ttvdm_gemm", p)
 
 
@@ -353,6 +355,10 @@ def layernorm(x, out, gamma, beta, *, rows, C, eps=1e-5, addvec=None, F=0, S=0, 
     p.gamma, p.beta, p.eps = _ptr(gamma), _ptr(beta), eps
     p.out, p.ldo = _ptr(out), C if ldo is None else ldo
     call("ttvdm_layernorm", p)
+
+
+def interleave2x(parts, out, *, n_img, H, W, C) -> None:
+    call_raw("ttvdm_interleave2x", c_void_p(_ptr(parts)), c_void_p(_ptr(out)), n_img, H, W, C)
 
 
 def im2col_s2(x, out, *, n_img, H, W, C) -> None:

@@ -76,6 +76,26 @@ def case_conv3x3(n=3, H=9, W=16, Cin=64, Cout=64, temb=True, fp32_out=False, see
     return rel_l2(out, ref)
 
 
+def case_upsample_conv(n=3, H=9, W=16, Cin=64, Cout=128, seed=0):
+    """Upsample2D (nearest x2 + 3x3 conv) as four 2x2-tap parity convolutions on the low-resolution input + interleave."""
+    from this_and_that_vdm_b200.engine import _pack_upsample_parity
+    x = bf(g(n, H, W, Cin, seed=seed))
+    w = bf(g(Cout, Cin, 3, 3, seed=seed + 1, scale=(9 * Cin) ** -0.5))
+    b = g(Cout, seed=seed + 2)
+    wp = _pack_upsample_parity(w, DEV)
+    M = n * H * W
+    parts = torch.empty(4, M, Cout, dtype=torch.bfloat16, device=DEV)
+    out = torch.empty(4 * M, Cout, dtype=torch.bfloat16, device=DEV)
+    for pi, (py, px) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        lib.gemm(x, wp[pi], parts[pi], M=M, N=Cout, k1=Cin, mode=lib.A_CONV3X3, n_img=n, H=H, W=W, bias=b, conv_taps=4,
+                 conv_dy0=py - 1, conv_dx0=px - 1)
+    lib.interleave2x(parts, out, n_img=n, H=H, W=W, C=Cout)
+    up = Fn.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = Fn.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(4 * M, Cout)
+    torch.cuda.synchronize()
+    return rel_l2(out, ref)
+
+
 def case_tconv(B=2, F=14, S=24, C=64, seed=0):
     x = bf(g(B, F, S, C, seed=seed))
     w = bf(g(C, C, 3, seed=seed + 1, scale=(3 * C) ** -0.5))  # [Cout, Cin, 3]
@@ -403,6 +423,9 @@ CASES = [
     ("conv3x3_stride2_L0", lambda: case_conv3x3(n=2, H=36, W=64, Cin=320, Cout=320, temb=False, stride=2)),
     ("conv3x3_stride2_odd_tiles", lambda: case_conv3x3(n=2, H=5, W=7, Cin=128, Cout=192, temb=False, stride=2)),
     ("conv3x3_stride2_L2", lambda: case_conv3x3(n=4, H=9, W=16, Cin=1280, Cout=1280, temb=False, stride=2)),
+    ("upsample_conv_small", lambda: case_upsample_conv()),
+    ("upsample_conv_odd", lambda: case_upsample_conv(n=2, H=5, W=7, Cin=128, Cout=64)),
+    ("upsample_conv_L1", lambda: case_upsample_conv(n=2, H=18, W=32, Cin=1280, Cout=1280)),
     ("conv3x3_L0", lambda: case_conv3x3(n=2, H=32, W=48, Cin=320, Cout=320)),
     ("conv3x3_wide", lambda: case_conv3x3(n=1, H=7, W=130, Cin=128, Cout=192)),
     ("conv3x3_out4_fp32", lambda: case_conv3x3(n=2, H=8, W=12, Cin=320, Cout=4, temb=False, fp32_out=True)),
