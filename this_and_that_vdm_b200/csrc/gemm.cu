@@ -531,8 +531,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (kCtas == 1) tma_load_2d(sa, ma, &full_bar[stage], ck, t.m0);
             else tma_load_2d_pair(sa, ma, &full_bar[stage], ck, t.m0);
           } else if (g.mode == TTVDM_A_CONV3X3) {
-            const int ty = tap / g.tap_w;
-            const int dy = ty + g.dy0, dx = tap - ty * g.tap_w + g.dx0;
+            // no runtime division here: this is ONE thread feeding the whole operand ring (a general `tap / tap_w` cost the
+            // level-0 / level-1 convolutions 20 % — the producer thread runs at one instruction per several cycles)
+            int ty, tx;
+            if (g.tap_w == 3) {
+              ty = tap / 3;
+              tx = tap - 3 * ty;
+            } else {
+              ty = tap >> 1;
+              tx = tap & 1;
+            }
+            const int dy = ty + g.dy0, dx = tx + g.dx0;
             const int cs = g.conv_stride;
             if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
             else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
