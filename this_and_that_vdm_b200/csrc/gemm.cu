@@ -516,45 +516,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int tile = sched_tile<kCtas>(g, ti, cta_rank);
       if (tile < 0) break;
       const TileCoord t = tile_coord(g, tile);
-      for (int kc = 0; kc < num_kc; ++kc) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        {
+      // tap / channel-chunk counters instead of kc / kc_per_tap: this is ONE thread feeding the whole operand ring, it runs
+      // at one instruction per several cycles next to the busy epilogue warps, and a stage of the level-0 shapes lasts
+      // only ~320 tensor-pipe cycles — every division here shows up in the GEMM time (a runtime `tap / tap_w` cost the
+      // level-0 / level-1 convolutions 20 %)
+      int kc = 0;
+      for (int tap = 0; tap < g.taps; ++tap) {
+        int ty, tx;
+        if (g.tap_w == 3) {
+          ty = tap / 3;
+          tx = tap - 3 * ty;
+        } else {
+          ty = tap >> 1;
+          tx = tap & 1;
+        }
+        const int cs = g.conv_stride;
+        const int ax = g.mode == TTVDM_A_CONV3X3 ? cs * t.w0 + tx + g.dx0 : t.w0;
+        const int ay = g.mode == TTVDM_A_CONV3X3 ? cs * t.h0 + ty + g.dy0 : t.h0 + tap - 1;
+        for (int cc = 0; cc < g.kc_per_tap; ++cc, ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * stage_bytes;
           uint8_t* sb = sa + kABytes;
           if (kCtas == 1) mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
           else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
-          const int tap = kc / g.kc_per_tap;
-          const int cc = kc - tap * g.kc_per_tap;
           if (g.mode == TTVDM_A_LINEAR) {
             const CUtensorMap* ma = (cc < g.kc_a1) ? &tmA : &tmA2;
             const int ck = (cc < g.kc_a1 ? cc : cc - g.kc_a1) * kBlockK;
             if (kCtas == 1) tma_load_2d(sa, ma, &full_bar[stage], ck, t.m0);
             else tma_load_2d_pair(sa, ma, &full_bar[stage], ck, t.m0);
-          } else if (g.mode == TTVDM_A_CONV3X3) {
-            // no runtime division here: this is ONE thread feeding the whole operand ring (a general `tap / tap_w` cost the
-            // level-0 / level-1 convolutions 20 % — the producer thread runs at one instruction per several cycles)
-            int ty, tx;
-            if (g.tap_w == 3) {
-              ty = tap / 3;
-              tx = tap - 3 * ty;
-            } else {
-              ty = tap >> 1;
-              tx = tap & 1;
-            }
-            const int dy = ty + g.dy0, dx = tx + g.dx0;
-            const int cs = g.conv_stride;
-            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
-            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, cs * t.w0 + dx, cs * t.h0 + dy, t.img);
           } else {
-            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
-            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, t.w0, t.h0 + tap - 1, t.img);
+            if (kCtas == 1) tma_load_4d(sa, &tmA, &full_bar[stage], cc * kBlockK, ax, ay, t.img);
+            else tma_load_4d_pair(sa, &tmA, &full_bar[stage], cc * kBlockK, ax, ay, t.img);
           }
           if (kCtas == 2) tma_load_2d_pair(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0 + cta_rank * (g.block_n >> 1));
           else if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
-        }
-        if (++stage == g.stages) {
-          stage = 0;
-          phase ^= 1;
+          if (++stage == g.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
