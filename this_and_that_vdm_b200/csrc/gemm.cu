@@ -335,7 +335,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         if (full) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+            const uint4 u = *(reinterpret_cast<const uint4*>(rp) + i);  // plain load: `out` may alias the residual
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -354,7 +354,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
         if (full) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+            const uint4 u = *(reinterpret_cast<const uint4*>(rp) + i);  // plain load: `out` may alias the residual
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -800,7 +800,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const __nv_bfloat16* rp = g.res2 + my_row * g.ldr2 + gc;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                const uint4 u = *(reinterpret_cast<const uint4*>(rp) + i);  // plain load: `out` may alias the residual
                 const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

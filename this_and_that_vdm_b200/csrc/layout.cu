@@ -59,10 +59,11 @@ __global__ void interleave2x_kernel(const uint4* __restrict__ parts, uint4* __re
   }
 }
 
-__global__ void axpy_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+// no __restrict__ / __ldg: `out` may alias `a` (the residual merge runs in place)
+__global__ void axpy_kernel(const uint4* a, const uint4* b, uint4* out,
                             float scale, long long n8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const uint4 ua = __ldg(a + i), ub = __ldg(b + i);
+    const uint4 ua = a[i], ub = b[i];
     const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
     uint32_t o[4];
 #pragma unroll
