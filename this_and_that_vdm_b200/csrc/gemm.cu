@@ -506,6 +506,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
     int stage = 0;
     uint32_t phase = 0;
+    uint8_t* sa_ring = tiles;
+    const uint32_t tx_bytes = kCtas == 1 ? (uint32_t)(g.b_resident ? kABytes : stage_bytes) : 2u * (uint32_t)stage_bytes;
     if (g.b_resident) {
       // the CTA's N tile of W: all K chunks, once
       const int n0 = (blockIdx.x % g.n_tiles) * g.block_n;
@@ -535,10 +537,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ay = g.mode == TTVDM_A_CONV3X3 ? cs * t.h0 + ty + g.dy0 : t.h0 + tap - 1;
         for (int cc = 0; cc < g.kc_per_tap; ++cc, ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = tiles + stage * stage_bytes;
+          uint8_t* sa = sa_ring;
           uint8_t* sb = sa + kABytes;
-          if (kCtas == 1) mbar_expect_tx(&full_bar[stage], g.b_resident ? kABytes : stage_bytes);
-          else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on the leader's barrier
+          if (kCtas == 1 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);  // pair: both CTAs' bytes land on the leader's barrier
           if (g.mode == TTVDM_A_LINEAR) {
             const CUtensorMap* ma = (cc < g.kc_a1) ? &tmA : &tmA2;
             const int ck = (cc < g.kc_a1 ? cc : cc - g.kc_a1) * kBlockK;
@@ -550,9 +551,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (kCtas == 2) tma_load_2d_pair(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0 + cta_rank * (g.block_n >> 1));
           else if (!g.b_resident) tma_load_2d(sb, &tmB, &full_bar[stage], kc * kBlockK, t.n0);
+          sa_ring += stage_bytes;
           if (++stage == g.stages) {
             stage = 0;
             phase ^= 1;
+            sa_ring = tiles;
           }
         }
       }
