@@ -24,6 +24,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional
 
+import os
+
 import torch
 
 from . import lib
@@ -89,6 +91,8 @@ class VaeEngine:
         if self.cfg.in_channels != 3 or self.cfg.out_channels != 3:
             raise lib.TtvdmError("sm_100a VAE engine supports RGB in / out (in_channels = out_channels = 3)")
         self.latent_channels = int(self.cfg.latent_channels)
+        # GroupNorm statistics from the producing GEMM's epilogue (round 2; TTVDM_VAE_FUSE_GN=0: standalone statistics pass)
+        self.fuse_norm_stats = os.environ.get("TTVDM_VAE_FUSE_GN", "1") != "0"
         self._pack(model)
 
     # ============================================================================================ packing
@@ -196,14 +200,18 @@ class VaeEngine:
         return [(i, min(n_img, i + per)) for i in range(0, n_img, per)]
 
     def _gn(self, x, gamma, beta, *, n_img, S, eps, silu, frames_per_inst=1):
-        """GroupNorm(32) (+SiLU). frames_per_inst = 1: per-image statistics; = F: the 5-D norm of TemporalResnetBlock."""
+        """GroupNorm(32) (+SiLU). frames_per_inst = 1: per-image statistics; = F: the 5-D norm of TemporalResnetBlock.
+        A tensor whose producing GEMM left per-(instance, channel pair) sums for this instance size (x.gn_stats, round 2)
+        needs no statistics pass: the call is the apply pass only."""
         C = x.shape[1]
         rows = n_img * S
         out = self._empty(rows, C)
-        if frames_per_inst > 1:
-            stats = self._empty((n_img // frames_per_inst) * 64, dtype=torch.float64)
-            lib.groupnorm(x, out, stats, gamma, beta, c1=C, rows=rows, rows_per_inst=frames_per_inst * S, eps=eps,
-                          silu=silu)
+        rpi = frames_per_inst * S
+        st = getattr(x, "gn_stats", None)
+        ps = st[0] if (st is not None and st[1] == rpi and (C // 32) % 2 == 0) else None
+        if frames_per_inst > 1 or ps is not None:
+            stats = None if ps is not None else self._empty((n_img // frames_per_inst) * 64, dtype=torch.float64)
+            lib.groupnorm(x, out, stats, gamma, beta, c1=C, rows=rows, rows_per_inst=rpi, eps=eps, silu=silu, pstats1=ps)
             return out
         for i0, i1 in self._groups(n_img, S, C):
             stats = self._empty((i1 - i0) * 64, dtype=torch.float64)
@@ -211,26 +219,50 @@ class VaeEngine:
                           rows_per_inst=S, eps=eps, silu=silu)
         return out
 
-    def _conv3(self, x, w, bias, *, n_img, H, W, cin, res1=None, out=None, out_fp32=False):
+    def _gn_sums(self, out, M: int, N: int, gn_rpi: int):
+        """Zeroed fp64 [M / gn_rpi, N / 2, 2] buffer for the epilogue of the GEMM that writes `out` (ttvdm_gemm
+        gn_stats_out) when its consumer is a GroupNorm over gn_rpi rows; rides on the tensor. None when not applicable."""
+        out.gn_stats = None
+        if not gn_rpi or not self.fuse_norm_stats or N % 64 != 0 or M % gn_rpi != 0 or out.dtype != BF16:
+            return None
+        st = torch.zeros((M // gn_rpi) * N, dtype=torch.float64, device=self.device)
+        out.gn_stats = (st, gn_rpi)
+        return st
+
+    def _conv3(self, x, w, bias, *, n_img, H, W, cin, res1=None, out=None, out_fp32=False, gn_rpi=0):
+        """gn_rpi: rows per GroupNorm instance of the CONSUMER of `out` (S: per image, F * S: the 5-D temporal norm): the
+        epilogue then leaves the statistics (whole instances per launch only)."""
         N = w.shape[0]
         S = H * W
         if out is None:
             out = self._empty(n_img * S, N, dtype=torch.float32 if out_fp32 else BF16)
+        st = self._gn_sums(out, n_img * S, N, gn_rpi)
         for i0, i1 in self._groups(n_img, S, max(cin, N)):
             sl = slice(i0 * S, i1 * S)
+            kw = {}
+            if st is not None:
+                if ((i0 * S) % gn_rpi) or ((i1 - i0) * S) % gn_rpi:
+                    out.gn_stats = None  # an instance would straddle two launches: leave it to the statistics pass
+                    st = None
+                else:
+                    kw = dict(gn_stats_out=st[(i0 * S // gn_rpi) * N:], gn_rows_per_inst=gn_rpi)
             lib.gemm(x[sl], w, out[sl], M=(i1 - i0) * S, N=N, k1=cin, mode=lib.A_CONV3X3, n_img=i1 - i0, H=H, W=W,
-                     bias=bias, res1=None if res1 is None else res1[sl], out_fp32=out_fp32)
+                     bias=bias, res1=None if res1 is None else res1[sl], out_fp32=out_fp32, **kw)
         return out
 
-    def _linear(self, a, w, *, M, bias=None, res1=None, out=None, out_fp32=False):
+    def _linear(self, a, w, *, M, bias=None, res1=None, out=None, out_fp32=False, gn_rpi=0):
         N, K = w.shape
         if out is None:
             out = self._empty(M, N, dtype=torch.float32 if out_fp32 else BF16)
+        st = self._gn_sums(out, M, N, gn_rpi)
         rows_per = max(1, _MAX_ELEMS // max(N, K))
+        if st is not None:
+            rows_per = max(gn_rpi, rows_per // gn_rpi * gn_rpi)  # whole instances per launch
         for r0 in range(0, M, rows_per):
             r1 = min(M, r0 + rows_per)
+            kw = dict(gn_stats_out=st[(r0 // gn_rpi) * N:], gn_rows_per_inst=gn_rpi) if st is not None else {}
             lib.gemm(a[r0:r1], w, out[r0:r1], M=r1 - r0, N=N, k1=K, bias=bias,
-                     res1=None if res1 is None else res1[r0:r1], out_fp32=out_fp32)
+                     res1=None if res1 is None else res1[r0:r1], out_fp32=out_fp32, **kw)
         return out
 
     # ============================================================================================ blocks
@@ -239,19 +271,25 @@ class VaeEngine:
         S = H * W
         rows = n_img * S
         y = self._gn(x, r.n1_g, r.n1_b, n_img=n_img, S=S, eps=1e-6, silu=True)
-        h = self._conv3(y, r.w1, r.b1, n_img=n_img, H=H, W=W, cin=r.cin)
+        h = self._conv3(y, r.w1, r.b1, n_img=n_img, H=H, W=W, cin=r.cin, gn_rpi=S)  # -> norm2 (per image)
         y = self._gn(h, r.n2_g, r.n2_b, n_img=n_img, S=S, eps=1e-6, silu=True)
         sc = x if r.wsc is None else self._linear(x, r.wsc, M=rows, bias=r.bsc)
-        hs = self._conv3(y, r.w2, r.b2, n_img=n_img, H=H, W=W, cin=r.cout, res1=sc, out=h)
+        # conv2 + shortcut feeds the temporal block's 5-D norm (F * S rows per instance) or the next block's per-image norm
+        hs = self._conv3(y, r.w2, r.b2, n_img=n_img, H=H, W=W, cin=r.cout, res1=sc, out=h,
+                         gn_rpi=(F * S if r.temporal else S))
         if not r.temporal:
             return hs
         B = n_img // F
         y = self._gn(hs, r.tn1_g, r.tn1_b, n_img=n_img, S=S, eps=1e-5, silu=True, frames_per_inst=F)
         t1 = self._empty(rows, r.cout)
-        lib.gemm(y, r.tw1, t1, M=rows, N=r.cout, k1=r.cout, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=r.tb1)
+        st = self._gn_sums(t1, rows, r.cout, F * S)  # -> tn2 (5-D)
+        kw = dict(gn_stats_out=st, gn_rows_per_inst=F * S) if st is not None else {}
+        lib.gemm(y, r.tw1, t1, M=rows, N=r.cout, k1=r.cout, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=r.tb1, **kw)
         y = self._gn(t1, r.tn2_g, r.tn2_b, n_img=n_img, S=S, eps=1e-5, silu=True, frames_per_inst=F)
+        st = self._gn_sums(t1, rows, r.cout, S)  # the blended output -> the next block's per-image norm
+        kw = dict(gn_stats_out=st, gn_rows_per_inst=S) if st is not None else {}
         lib.gemm(y, r.tw2, t1, M=rows, N=r.cout, k1=r.cout, mode=lib.A_TCONV3, n_img=B, H=F, W=S, bias=r.tb2,
-                 s0=r.t_scale, res1=hs, s1=1.0)
+                 s0=r.t_scale, res1=hs, s1=1.0, **kw)
         return t1
 
     def _attention(self, a: VAttnW, x, *, n_img, H, W):
@@ -276,7 +314,7 @@ class VaeEngine:
             lib.gemm(q[sl], k[sl], scores, M=S, N=S, k1=C, s0=scale, out_fp32=True)
             lib.softmax_rows(scores, probs, rows=S, cols=S, ldx=S, ldo=Sp, cols_out=Sp)
             lib.gemm(probs, vt, o[sl], M=S, N=C, k1=Sp, bias=a.bv)  # + b_v: rows of P sum to one
-        return self._linear(o, a.wo, M=rows, bias=a.bo, res1=x, out=q)
+        return self._linear(o, a.wo, M=rows, bias=a.bo, res1=x, out=q, gn_rpi=S)  # -> the next ResBlock's norm1
 
     # ============================================================================================ boundary API
     def _to_tokens(self, t: torch.Tensor, pad_to: int) -> torch.Tensor:
@@ -322,7 +360,8 @@ class VaeEngine:
 
     def _encode_pass(self, x: torch.Tensor) -> torch.Tensor:
         n, _, H, W = x.shape
-        h = self._conv3(self._to_tokens(x, PAD_IN), self.e_conv_in_w, self.e_conv_in_b, n_img=n, H=H, W=W, cin=PAD_IN)
+        h = self._conv3(self._to_tokens(x, PAD_IN), self.e_conv_in_w, self.e_conv_in_b, n_img=n, H=H, W=W, cin=PAD_IN,
+                        gn_rpi=H * W)
         for blk in self.e_down:
             for r in blk["res"]:
                 h = self._resblock(r, h, n_img=n, F=1, H=H, W=W)
@@ -331,7 +370,7 @@ class VaeEngine:
                 col = self._empty(n * (H // 2) * (W // 2), 9 * C)
                 lib.im2col_s2_pad01(h, col, n_img=n, H=H, W=W, C=C)
                 H, W = H // 2, W // 2
-                h = self._linear(col, blk["down_w"], M=n * H * W, bias=blk["down_b"])
+                h = self._linear(col, blk["down_w"], M=n * H * W, bias=blk["down_b"], gn_rpi=H * W)
         h = self._resblock(self.e_mid_res[0], h, n_img=n, F=1, H=H, W=W)
         h = self._attention(self.e_mid_attn, h, n_img=n, H=H, W=W)
         h = self._resblock(self.e_mid_res[1], h, n_img=n, F=1, H=H, W=W)
@@ -349,7 +388,8 @@ class VaeEngine:
             raise ValueError(f"{n} latent frames are not a multiple of num_frames={num_frames}")
         F = num_frames
         kw = dict(n_img=n, F=F)
-        h = self._conv3(self._to_tokens(z, PAD_IN), self.d_conv_in_w, self.d_conv_in_b, n_img=n, H=H, W=W, cin=PAD_IN)
+        h = self._conv3(self._to_tokens(z, PAD_IN), self.d_conv_in_w, self.d_conv_in_b, n_img=n, H=H, W=W, cin=PAD_IN,
+                        gn_rpi=H * W)
         h = self._resblock(self.d_mid_res[0], h, H=H, W=W, **kw)
         for att, r in zip(self.d_mid_attn, self.d_mid_res[1:]):
             h = self._attention(att, h, n_img=n, H=H, W=W)
@@ -364,7 +404,7 @@ class VaeEngine:
                 for i0, i1 in self._groups(n, 4 * S, C):
                     lib.upsample2x(h[i0 * S:i1 * S], up[i0 * 4 * S:i1 * 4 * S], n_img=i1 - i0, H=H, W=W, C=C)
                 H, W = 2 * H, 2 * W
-                h = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n, H=H, W=W, cin=C)
+                h = self._conv3(up, blk["up_w"], blk["up_b"], n_img=n, H=H, W=W, cin=C, gn_rpi=H * W)
                 del up
         y = self._gn(h, self.d_out_g, self.d_out_b, n_img=n, S=H * W, eps=1e-6, silu=True)
         rgb = self._conv3(y, self.d_conv_out_w, self.d_conv_out_b, n_img=n, H=H, W=W, cin=h.shape[1], out_fp32=True)
