@@ -199,3 +199,29 @@ def test_25_frames_svd_xt_schedule_vs_oracle(tiny):
         ref = O.unet_forward(usd, cfg, sample, T0, ehs, ati)
     assert out.shape == ref.shape == (2, 25, 4, 8, 8)
     assert rel_l2(out, ref) < CAP
+
+
+def test_upsample_parity_weights_identity_fp32():
+    """conv3x3(nearest_x2(x), w, padding=1) == the four 2x2-tap parity convolutions of x with the pre-summed weights of
+    engine._pack_upsample_parity, interleaved — checked in plain fp32 torch (no kernels, no emulation): pins the tap
+    grouping ({y-1: ky 0, y: ky 1+2} for even output rows, {y: ky 0+1, y+1: ky 2} for odd ones)."""
+    import torch.nn.functional as Fn
+    g = torch.Generator().manual_seed(5)
+    n, C, N, H, W = 2, 6, 5, 5, 7
+    x = torch.randn(n, C, H, W, generator=g)
+    w = torch.randn(N, C, 3, 3, generator=g)
+    ref = Fn.conv2d(Fn.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = torch.zeros(n, N, 2 * H, 2 * W)
+    for py in (0, 1):
+        for px in (0, 1):
+            wp = torch.zeros(N, C, 2, 2)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    for ky in groups[py][ty]:
+                        for kx in groups[px][tx]:
+                            wp[:, :, ty, tx] += w[:, :, ky, kx]
+            # window whose first tap sits at (py - 1, px - 1) relative to the output pixel: pad accordingly
+            xp = Fn.pad(x, (1 - px, px, 1 - py, py))
+            out[:, :, py::2, px::2] = Fn.conv2d(xp, wp)
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
